@@ -1,0 +1,257 @@
+"""CPU oracle for the batched-LP hot path of tulip-control/polytope.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``polytope_b200/`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` do, and there only as the checker or
+as the CPU arm being timed -- never as the product path.
+
+What it restates (all citations relative to /root/reference):
+
+* ``lpsolve``            -- polytope/solvers.py:76-106, scipy adapter :149-158
+* ``normalize_rows``     -- Polytope.__init__, polytope/polytope.py:122-138
+* ``cheby_ball``         -- polytope/polytope.py:1241-1300
+* ``is_fulldim``         -- polytope/polytope.py:962-985
+* ``bounding_box``       -- polytope/polytope.py:1314-1411
+* ``reduce``             -- polytope/polytope.py:1053-1163
+* ``intersect``          -- Polytope.intersect, polytope/polytope.py:255-275
+* ``is_adjacent``        -- polytope/polytope.py:1827-1866 (overlap=True branch)
+* ``adjacency_matrix``   -- prop2partition.py:46-63 (find_adjacent_regions)
+
+The arithmetic of the path lives in a third-party dependency that is NOT
+vendored under /root/reference: ``scipy.optimize.linprog`` -> HiGHS
+(reference pins scipy==1.10.0, requirements/default.txt:2; this image has
+scipy 1.18.1 / HiGHS 1.12.0, inside the range pyproject.toml:28-32 allows).
+The oracle therefore calls the same ``linprog`` entry with the same arguments
+the reference does and restates only the reference's own numpy logic around it.
+
+Parity pinning: ``tests/golden/make_golden.py`` imports the unmodified
+reference from /root/reference in the build container, records its outputs on
+seeded inputs (including the inputs of the reference's own tests) and
+``tests/test_oracle.py`` asserts this module reproduces them bit for bit.
+
+Data model: a polytope is a pair ``(A, b)`` of float64 arrays (m x d, m); the
+reference's ``Polytope`` object is not rebuilt here.  Every function returns
+plain arrays / index lists so results can be compared element by element.
+"""
+import numpy as np
+from scipy import optimize
+
+ABS_TOL = 1e-7  # polytope/polytope.py:83
+
+# number of LPs solved since the last reset (the unit BASELINE.json's metric
+# counts: one lpsolve-equivalent solve the reference algorithm requires)
+lp_count = 0
+
+
+def lpsolve(c, G, h):
+    """min c'x s.t. Gx <= h, x free.  solvers.py:149-158."""
+    global lp_count
+    lp_count += 1
+    sol = optimize.linprog(c, G, np.transpose(h), None, None,
+                           bounds=(None, None))
+    return dict(status=sol.status, x=sol.x, fun=sol.fun)
+
+
+def normalize_rows(A, b):
+    """Row normalisation of Polytope.__init__ (polytope.py:122-138).
+
+    Returns (A_n, b_n, pos): the normalised float64 copies and the indices of
+    the input rows that survive (rows with 2-norm <= 1e-10 are dropped).
+    """
+    A = np.asarray(A)
+    b = np.asarray(b)
+    An = A.astype(float)
+    bn = b.astype(float).flatten()
+    pos = np.arange(An.shape[0]) if An.ndim == 2 else np.arange(0)
+    if A.size > 0:
+        # the norm is taken on the caller's array (its dtype), :129
+        nrm = np.sqrt(np.sum(A * A, 1)).flatten()
+        pos = np.nonzero(nrm > 1e-10)[0]
+        An = An[pos, :]
+        bn = bn[pos]
+        mult = 1 / nrm[pos]
+        An = An * mult[:, None]      # same products as the row loop :136-137
+        bn = bn * mult
+    return An, bn, pos
+
+
+def cheby_lp_data(A, b):
+    """(c, G, h) of the Chebyshev LP, polytope.py:1283-1287."""
+    c = np.negative(np.r_[np.zeros(A.shape[1]), 1])
+    G = np.c_[A, np.sqrt(np.sum(A * A, axis=1))]
+    return c, G, b
+
+
+def cheby_ball(A, b):
+    """Chebyshev radius/centre of {x: Ax<=b} (polytope.py:1241-1300).
+
+    Returns (r, xc); (0, None) when A has no rows, the LP is not optimal or the
+    radius is negative.  (A, b) is used as given (no normalisation here: the
+    reference object was normalised by its constructor).
+    """
+    if len(A) == 0:                     # is_empty, :939-948
+        return 0, None
+    c, G, h = cheby_lp_data(A, b)
+    sol = lpsolve(c, G, h)
+    if sol['status'] == 0:
+        r = sol['x'][-1]
+        if r < 0:
+            return 0, None
+        return np.double(r), np.array(sol['x'][0:-1])
+    return 0, None
+
+
+def is_fulldim(A, b, abs_tol=ABS_TOL):
+    """polytope.py:962-985 for a single polytope."""
+    r, _ = cheby_ball(A, b)
+    return bool(r > abs_tol)
+
+
+def bounding_box(A, b):
+    """(l, u) column vectors, polytope.py:1362-1411."""
+    m, n = np.shape(A)
+    l = np.zeros([n, 1])
+    u = np.zeros([n, 1])
+    for sign, out in ((1.0, l), (-1.0, u)):
+        for i in range(n):
+            c = np.zeros(n)
+            c[i] = sign
+            sol = lpsolve(c, A, b)
+            st = sol['status']
+            if st == 0:
+                out[i] = sol['x'][i]
+            elif st == 3:
+                out[i] = -sign * np.inf
+            elif st == 2:
+                out[i] = 0 if sign > 0 else l[i]
+            else:
+                raise RuntimeError('bounding_box: lpsolve returned %r' % sol)
+    return l, u
+
+
+def duplicate_rows(A, b, abs_tol=ABS_TOL):
+    """Rows `reduce` removes as parallel duplicates, polytope.py:1094-1110.
+
+    Returns the sorted unique kept indices (what np.setdiff1d gives).
+    """
+    neq = A.shape[0]
+    a_norm = 1 / np.sqrt(np.sum(A.T**2, 0))
+    a_normed = np.dot(A.T, np.diag(a_norm)).T
+    removed = []
+    for i in range(neq):
+        for j in range(i + 1, neq):
+            if np.dot(a_normed[i].T, a_normed[j]) > 1 - abs_tol:
+                if b[i] * a_norm[i] < b[j] * a_norm[j]:
+                    removed.append(j)
+                else:
+                    removed.append(i)
+    return np.setdiff1d(range(neq), removed).tolist()
+
+
+def bbox_candidates(A, b, lb, ub):
+    """Boolean mask of rows that may touch the bounding box, :1118-1132."""
+    cand = ~(np.dot((A > 0) * A, ub - lb)
+             - (np.array([b]).T - np.dot(A, lb)) < -1e-4)
+    return cand.squeeze()
+
+
+def reduce(A, b, abs_tol=ABS_TOL, normalize=True):
+    """Redundant-row removal, polytope.py:1053-1163, on raw (A, b).
+
+    Returns a dict:
+      empty   -- True when the reference returns the empty Polytope() (:1082)
+      keep    -- indices (into the INPUT rows) of the rows the reference keeps
+      A, b    -- the arrays handed to the final Polytope(...) constructor
+                 (b carries the reference's +0.1/-0.1 one-ulp drift, :1149-1151)
+      minrep  -- value of the returned object's `minrep`
+      r, xc   -- Chebyshev ball found by the leading is_fulldim() call
+      n_lp    -- LPs this call solved
+    """
+    global lp_count
+    lp0 = lp_count
+    if normalize:
+        A, b, idx = normalize_rows(A, b)
+    else:
+        A = np.array(A, dtype=float)
+        b = np.array(b, dtype=float).flatten()
+        idx = np.arange(A.shape[0])
+    r, xc = cheby_ball(A, b)
+    out = dict(empty=False, keep=[], A=None, b=None, minrep=False,
+               r=r, xc=xc, n_lp=0)
+    if not r > ABS_TOL:                 # is_fulldim(poly) uses its default, :1081
+        out['empty'] = True
+        out['n_lp'] = lp_count - lp0
+        return out
+    fin = np.nonzero(b != np.inf)[0]                      # :1087-1089
+    A, b, idx = A[fin], b[fin], idx[fin]
+    keep = duplicate_rows(A, b, abs_tol)                  # :1094-1112
+    A, b, idx = A[keep], b[keep], idx[keep]
+    neq, nx = A.shape
+    done = neq <= nx + 1                                  # :1114-1116
+    if not done and neq > 3 * nx:                         # :1118-1134
+        An, bn, _ = normalize_rows(A, b)                  # Polytope(A_arr,b_arr)
+        lb, ub = bounding_box(An, bn)
+        cand = bbox_candidates(A, b, lb, ub)
+        A, b, idx = A[cand], b[cand], idx[cand]
+        neq, nx = A.shape
+    done = done or neq <= nx + 1                          # :1135-1138
+    if done:
+        out.update(keep=idx.tolist(), A=A, b=b, n_lp=lp_count - lp0)
+        return out
+    kept = []
+    h = b                                                 # aliased, as in :1147
+    for k in range(neq):                                  # :1142-1160
+        h[k] += 0.1
+        sol = lpsolve(-A[k, :], A, h)
+        h[k] -= 0.1
+        if sol['status'] == 0:
+            if (-sol['fun'] - h[k]) > abs_tol:
+                kept.append(k)
+        elif sol['status'] == 3:
+            kept.append(k)
+    out.update(keep=idx[kept].tolist(), A=A[kept], b=b[kept], minrep=True,
+               n_lp=lp_count - lp0)
+    return out
+
+
+def intersect(A1, b1, A2, b2, abs_tol=ABS_TOL):
+    """Polytope.intersect, polytope.py:255-275, on normalised operands.
+
+    Returns the `reduce` dict of the stacked system (empty=True when either
+    operand is not full-dimensional, :268-269); `keep` indexes the stacked rows.
+    """
+    if not is_fulldim(A1, b1) or not is_fulldim(A2, b2):
+        return dict(empty=True, keep=[], A=None, b=None, minrep=False,
+                    r=0, xc=None, n_lp=2)
+    if A1.shape[1] != A2.shape[1]:
+        raise Exception('polytopes have different dimension')
+    return reduce(np.vstack([A1, A2]), np.hstack([b1, b2]), abs_tol=abs_tol)
+
+
+def adjacent_lp_data(A1, b1, A2, b2, abs_tol=ABS_TOL):
+    """Stacked, inflated, re-normalised system of is_adjacent, :1856-1865."""
+    A = np.concatenate((A1, A2))
+    b = np.concatenate((b1 + abs_tol, b2 + abs_tol))
+    An, bn, _ = normalize_rows(A, b)
+    return An, bn
+
+
+def is_adjacent(A1, b1, A2, b2, abs_tol=ABS_TOL):
+    """polytope.py:1827-1866, overlap=True, two single polytopes."""
+    An, bn = adjacent_lp_data(A1, b1, A2, b2, abs_tol)
+    return is_fulldim(An, bn, abs_tol=abs_tol / 10)
+
+
+def adjacency_matrix(cells, abs_tol=ABS_TOL):
+    """find_adjacent_regions, prop2partition.py:46-63, over single polytopes.
+
+    `cells` is a list of normalised (A, b); returns a dense int8 matrix.
+    """
+    n = len(cells)
+    adj = np.zeros((n, n), dtype=np.int8)
+    for i in range(n):
+        adj[i, i] = 1
+        for j in range(i):
+            adj[i, j] = adj[j, i] = is_adjacent(*cells[i], *cells[j],
+                                                abs_tol=abs_tol)
+    return adj

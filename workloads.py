@@ -1,0 +1,60 @@
+"""Synthetic workloads named by BASELINE.json / SURVEY.md section 8(d).
+
+Shared by bench.py, the tests and tests/golden/make_golden.py so that the GPU
+arm, the CPU arm and the golden fixtures all see identical (A, b) inputs.
+Pure numpy; no reference or oracle import.
+"""
+import numpy as np
+
+
+def box_cuts(seed, m, d, shift_scale=False):
+    """G1 "box+cuts": the box [-1,1]^d plus m-2d random unit-normal cuts
+    a.x <= t*||a||_1, t ~ U(0.6, 1.4), rows permuted.
+    A cut with t >= 1 is redundant w.r.t. the box by construction.
+    """
+    rng = np.random.default_rng(seed)
+    k = m - 2 * d
+    if k < 0:
+        raise ValueError('box_cuts needs m >= 2d')
+    C = rng.standard_normal((k, d))
+    C /= np.sqrt(np.sum(C * C, axis=1))[:, None]
+    t = rng.uniform(0.6, 1.4, k)
+    A = np.vstack([np.eye(d), -np.eye(d), C])
+    b = np.hstack([np.ones(2 * d), t * np.sum(np.abs(C), axis=1)])
+    perm = rng.permutation(m)
+    A, b = A[perm], b[perm]
+    if shift_scale:
+        x0 = rng.uniform(-1, 1, d)
+        s = rng.uniform(0.3, 1.0)
+        b = s * b + A @ x0
+    return np.ascontiguousarray(A), np.ascontiguousarray(b)
+
+
+def box_cuts_batch(cfg, n_poly, m, d, shift_scale=False, first=0):
+    """Stacked batch: polytope i uses seed 1000*cfg + i."""
+    A = np.empty((n_poly, m, d))
+    b = np.empty((n_poly, m))
+    for i in range(n_poly):
+        A[i], b[i] = box_cuts(1000 * cfg + first + i, m, d, shift_scale)
+    return A, b
+
+
+def box_grid(shape, origin=0.0, cell=1.0):
+    """Regular grid of axis-aligned boxes as rows [I; -I] x <= [hi; -lo]
+    (cfg5: prop2partition adjacency).  Returns (A[n,2d,d], b[n,2d], index[n,d]).
+    """
+    shape = tuple(shape)
+    d = len(shape)
+    idx = np.stack(np.meshgrid(*[np.arange(s) for s in shape],
+                               indexing='ij'), -1).reshape(-1, d)
+    lo = origin + cell * idx
+    hi = lo + cell
+    n = idx.shape[0]
+    A = np.broadcast_to(np.vstack([np.eye(d), -np.eye(d)]), (n, 2 * d, d)).copy()
+    b = np.hstack([hi, -lo])
+    return A, b, idx
+
+
+def unit_cube3():
+    """cfg1: Polytope(vstack(I3,-I3), [1,1,1,0,0,0]) (not from_box)."""
+    return np.vstack([np.eye(3), -np.eye(3)]), np.array([1., 1, 1, 0, 0, 0])
