@@ -1,0 +1,130 @@
+/* polytope_b200 -- C ABI of the B200 batched-LP engine.
+ *
+ * Drop-in boundary for the LP hot path of tulip-control/polytope.  Each entry
+ * point cites the reference interface (file:line under /root/reference) whose
+ * loop of one-at-a-time `lpsolve` calls it replaces.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *     the caller owns all buffers, nothing is allocated or freed inside;
+ *   - matrices are C-order (row-major) float64, exactly numpy's default;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
+ *     work is stream-ordered and asynchronous, results are valid after the
+ *     caller synchronises the stream;
+ *   - return value: 0 on success, a negative PB200_E* code otherwise; nothing
+ *     ever throws across the ABI.  pb200_last_error() describes the last failure
+ *     of the calling thread;
+ *   - LP status bytes use scipy.optimize.linprog's convention, which is what
+ *     polytope/solvers.py:92-93 documents: 0 optimal, 1 iteration limit,
+ *     2 infeasible, 3 unbounded, 4 numerical trouble.
+ *   - supported sizes: 1 <= n <= 32 columns, 1 <= m <= 128 rows per LP
+ *     (the reduce / adjacency pipelines additionally need m <= 64 because row
+ *     sets travel as 64-bit masks).  Anything else returns PB200_EUNSUPPORTED.
+ */
+#ifndef POLYTOPE_B200_H
+#define POLYTOPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_OK 0
+#define PB200_EINVAL (-1)        /* bad argument (null pointer, negative size) */
+#define PB200_EUNSUPPORTED (-2)  /* size outside the kernel envelope */
+#define PB200_ECUDA (-3)         /* a CUDA call failed; see pb200_last_error() */
+#define PB200_EWORKSPACE (-4)    /* workspace too small */
+
+/* flag bits written by pb200_reduce_batch into flags[p] */
+#define PB200_F_EMPTY 1u      /* not full-dimensional: reference returns Polytope() (polytope.py:1081-1082) */
+#define PB200_F_MINREP 2u     /* went through the per-row LP loop: result has minrep=True (:1161-1162) */
+#define PB200_F_BBOX 4u       /* bounding-box prefilter ran (:1118-1134) */
+#define PB200_F_LPFAIL 8u     /* some LP ended with status 1/4 (reference: silently drops the row in reduce, raises in bounding_box) */
+
+const char* pb200_version(void);
+const char* pb200_last_error(void);
+
+/* B independent LPs  min c'x s.t. Gx <= h, x free.
+ * Replaces: polytope.solvers.lpsolve(c, G, h), polytope/solvers.py:76-106,
+ * called once per LP (scipy adapter :149-158).
+ *   G[B][m][n], h[B][m], c[B][n]; m_rows[B] (nullable) = rows actually used by
+ *   LP i (ragged batches; rows >= m_rows[i] are ignored).
+ *   x[B][n], fun[B] (valid where status == 0), status[B], iters[B] (nullable). */
+int pb200_lp_batch(const double* G, const double* h, const double* c,
+                   const int32_t* m_rows, int B, int m, int n,
+                   double* x, double* fun, int8_t* status, int32_t* iters,
+                   void* stream);
+
+/* Row normalisation of the Polytope constructor for P stacked polytopes.
+ * Replaces: Polytope.__init__, polytope/polytope.py:128-138 (norm in numpy's
+ * summation order, rows with norm <= 1e-10 dropped).
+ *   A[P][m][d], b[P][m] in; An, bn out (same shapes); valid[P] = bit i set iff
+ *   row i survives (m <= 64).  m_rows nullable as above. */
+int pb200_normalize_batch(const double* A, const double* b, const int32_t* m_rows,
+                          int P, int m, int d, double* An, double* bn,
+                          uint64_t* valid, void* stream);
+
+/* Chebyshev ball LP of P polytopes used as given (no normalisation).
+ * Replaces: cheby_ball, polytope/polytope.py:1280-1300 (and is_fulldim :962-985,
+ * which thresholds the radius).
+ *   rows[P] nullable: bit mask of the rows to use (default: the first m_rows[p]
+ *   or m rows).  r[P] = x[-1] of the LP, xc[P][d] = x[:-1], status[P]. */
+int pb200_cheby_batch(const double* A, const double* b, const int32_t* m_rows,
+                      const uint64_t* rows, int P, int m, int d,
+                      double* r, double* xc, int8_t* status, void* stream);
+
+/* Bounding boxes: 2d LPs per polytope.
+ * Replaces: bounding_box, polytope/polytope.py:1362-1411 (status 3 -> -/+inf,
+ * status 2 -> l = 0, u = l).  lo[P][d], hi[P][d]; status[P][2d] raw LP statuses. */
+int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows,
+                     int P, int m, int d, double* lo, double* hi, int8_t* status,
+                     void* stream);
+
+/* Batched reduce(): redundant-row removal for P polytopes given as RAW (A, b),
+ * i.e. what `reduce(Polytope(A, b))` computes.
+ * Replaces: reduce, polytope/polytope.py:1053-1163, including the constructor
+ * normalisation (:128-138), is_fulldim (:1081), the b == inf drop (:1087-1089),
+ * the duplicate-direction filter (:1094-1112), both early exits (:1114-1116,
+ * :1135-1138), the bounding-box prefilter (:1118-1134) and the per-row LP loop
+ * (:1142-1160) with its +0.1/-0.1 one-ulp drift of b.
+ *   normalize != 0: (A, b) are raw constructor arguments; == 0: they are the
+ *             .A/.b of an existing Polytope and are used as they are
+ *   keep[P]   bit i set iff input row i is kept
+ *   flags[P]  PB200_F_* bits
+ *   r[P], xc[P][d]  Chebyshev ball of the input (first is_fulldim call)
+ *   b_out[P][m]     constructor-normalised b after the reference's drift
+ *   A_out[P][m][d]  constructor-normalised A (nullable)
+ *   n_lp[P]         LPs the reference algorithm solves for this polytope
+ *   workspace: pb200_reduce_workspace_bytes(P, m, d) bytes of device memory. */
+size_t pb200_reduce_workspace_bytes(int P, int m, int d);
+int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows,
+                       int P, int m, int d, double abs_tol, int normalize,
+                       uint64_t* keep, uint32_t* flags, double* r, double* xc,
+                       double* b_out, double* A_out, int32_t* n_lp,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* is_adjacent() over T pairs of cells (single polytopes, already normalised by
+ * the constructor).
+ * Replaces: is_adjacent overlap=True branch, polytope/polytope.py:1856-1866,
+ * driven by find_adjacent_regions / compute_adj, prop2partition.py:46-63,
+ * :244-261: stack both cells, add abs_tol to b, re-normalise, Chebyshev LP,
+ * flag = radius > abs_tol/10.
+ *   A[ncell][mc][d], b[ncell][mc]; pair_i/pair_j[T] or both NULL for the
+ *   lower-triangular enumeration t -> (i, j), j < i, of find_adjacent_regions
+ *   (then T must be ncell*(ncell-1)/2).  adjacent[T] (0/1), radius[T] nullable. */
+int pb200_adjacent_pairs(const double* A, const double* b, int ncell, int mc, int d,
+                         const int32_t* pair_i, const int32_t* pair_j, long long T,
+                         double abs_tol, uint8_t* adjacent, double* radius,
+                         int8_t* status, void* stream);
+
+/* Number of kernels this library has launched since load (bench.py's
+ * `gpu_launches` evidence). */
+long long pb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLYTOPE_B200_H */

@@ -1,0 +1,64 @@
+"""ctypes binding of libpolytope_b200.so (C ABI: include/polytope_b200.h).
+
+The library is the product; there is no Python/numpy/CPU fallback.  Importing
+this module on a box where the library has not been built, or calling into it
+without a CUDA device, raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpolytope_b200.so')
+
+c_void_p, c_int, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+c_size_t, c_longlong, c_char_p = ctypes.c_size_t, ctypes.c_longlong, ctypes.c_char_p
+
+# name -> (restype, argtypes); mirrors include/polytope_b200.h one to one
+SIGNATURES = {
+    'pb200_version': (c_char_p, []),
+    'pb200_last_error': (c_char_p, []),
+    'pb200_launch_count': (c_longlong, []),
+    'pb200_lp_batch': (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 5),
+    'pb200_normalize_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p] * 4),
+    'pb200_cheby_batch': (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 4),
+    'pb200_bbox_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p] * 4),
+    'pb200_reduce_workspace_bytes': (c_size_t, [c_int] * 3),
+    'pb200_reduce_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_double, c_int]
+                           + [c_void_p] * 8 + [c_size_t, c_void_p]),
+    'pb200_adjacent_pairs': (c_int, [c_void_p] * 2 + [c_int] * 3 + [c_void_p] * 2
+                             + [c_longlong, c_double] + [c_void_p] * 4),
+}
+
+
+class Pb200Error(RuntimeError):
+    pass
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise Pb200Error(
+            'polytope_b200: %s is missing -- build it with '
+            '`python -c "import __graft_entry__ as g; g.build()"` or '
+            '`make -C polytope_b200/csrc`.  There is no CPU fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = load()
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise Pb200Error('%s failed (%d): %s' % (
+            what, rc, lib().pb200_last_error().decode()))

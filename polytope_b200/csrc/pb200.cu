@@ -1,0 +1,808 @@
+// polytope_b200: kernels around the warp LP solver and the C ABI
+// (include/polytope_b200.h).  sm_100a only.
+//
+// Every LP-solving kernel is the same persistent "one LP per warp" loop,
+// parameterised by a Problem type that knows how to stage (c, G, h) of work
+// item t into the warp's shared-memory scratch and what to do with the result:
+//
+//   GenericLP    lpsolve(c, G, h)                       polytope/solvers.py:76-106
+//   ChebyLP      cheby_ball                              polytope/polytope.py:1280-1300
+//   BboxLP       bounding_box (2d LPs per polytope)      polytope/polytope.py:1362-1411
+//   RowLP        reduce()'s per-row redundancy LP        polytope/polytope.py:1142-1160
+//   AdjacentLP   is_adjacent (stack, inflate, cheby)     polytope/polytope.py:1856-1866
+//
+// Each warp stages its own copy of the (tiny) constraint matrix; LPs of the
+// same polytope re-read it from L2, which keeps HBM traffic at the algorithmic
+// bytes while leaving no warp idle (a whole cfg2 batch is 23 MB, L2 is 126 MB).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/polytope_b200.h"
+#include "lp_warp.cuh"
+
+namespace pb200 {
+
+constexpr int WPC = 4;                  // warps per CTA of the LP kernels
+static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+
+#define PB_CHECK_CUDA(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            snprintf(g_err, sizeof(g_err), "%s failed: %s (%s:%d)", #expr,                \
+                     cudaGetErrorString(e__), __FILE__, __LINE__);                        \
+            return PB200_ECUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+static int fail(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+
+// ------------------------------------------------------------------------
+// numpy-order arithmetic.  np.sum over a contiguous axis uses pairwise
+// summation with 8 accumulators (numpy/_core/src/umath/loops_utils.h.src,
+// *_pairwise_sum); for n <= 128 that is the code below.  The reference
+// computes every row norm that way (polytope.py:129, :1094, :1285), and
+// tests/test_gpu_normalize.py checks bit-equality against numpy.
+// ------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ double np_sum_squares(F elem, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int j = 0; j < n; ++j) { const double a = elem(j); res = __dadd_rn(res, __dmul_rn(a, a)); }
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const double a = elem(j); r[j] = __dmul_rn(a, a); }
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const double a = elem(i + j); r[j] = __dadd_rn(r[j], __dmul_rn(a, a)); }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) { const double a = elem(i); res = __dadd_rn(res, __dmul_rn(a, a)); }
+    return res;
+}
+
+__device__ __forceinline__ uint64_t low_bits(int m) { return m >= 64 ? ~0ull : ((1ull << m) - 1ull); }
+
+// index of the k-th (0-based) set bit of mask; mask must have > k bits set
+__device__ __forceinline__ int nth_set_bit(uint64_t mask, int k) {
+    for (int i = 0; i < k; ++i) mask &= mask - 1;
+    return __ffsll((long long)mask) - 1;
+}
+
+// ------------------------------------------------------------------------
+// staging helpers (one warp)
+// ------------------------------------------------------------------------
+template <int RPL>
+__device__ __forceinline__ void zero_G(const WarpScratch& w, int ncols, int lane) {
+    for (int e = lane; e < ncols * w.MP; e += 32) w.G[e] = 0.0;
+    __syncwarp();
+}
+
+// rows [0, cnt) of a row-major [.. x ld] matrix -> column-major slots; h from bp
+template <int RPL>
+__device__ __forceinline__ void stage_first_rows(const WarpScratch& w, const double* __restrict__ Ap,
+                                                 const double* __restrict__ bp, int cnt, int d, int ncols,
+                                                 int lane, double (&h)[RPL]) {
+    zero_G<RPL>(w, ncols, lane);
+    const int total = cnt * d;
+    for (int e = lane; e < total; e += 32) {
+        const int i = e / d, j = e - i * d;
+        w.G[j * w.MP + i] = __ldg(Ap + e);
+    }
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int i = lane + 32 * r;
+        h[r] = i < cnt ? __ldg(bp + i) : 0.0;
+    }
+    __syncwarp();
+}
+
+// rows selected by `mask` (ascending) of a row-major [m x d] matrix -> slots 0..cnt-1
+template <int RPL>
+__device__ __forceinline__ int stage_masked_rows(const WarpScratch& w, const double* __restrict__ Ap,
+                                                 const double* __restrict__ bp, int m, int d, int ncols,
+                                                 uint64_t mask, int lane, double (&h)[RPL]) {
+    zero_G<RPL>(w, ncols, lane);
+    const int total = m * d;
+    for (int e = lane; e < total; e += 32) {
+        const int i = e / d, j = e - i * d;
+        if ((mask >> i) & 1ull) {
+            const int slot = __popcll(mask & ((1ull << i) - 1ull));
+            w.G[j * w.MP + slot] = __ldg(Ap + e);
+        }
+    }
+    for (int i = lane; i < m; i += 32)
+        if ((mask >> i) & 1ull) w.d[__popcll(mask & ((1ull << i) - 1ull))] = __ldg(bp + i);
+    __syncwarp();
+    const int cnt = __popcll(mask);
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int i = lane + 32 * r;
+        h[r] = i < cnt ? w.d[i] : 0.0;
+    }
+    __syncwarp();
+    return cnt;
+}
+
+// Polytope.__init__ normalisation of the staged rows (polytope.py:128-138):
+// row / ||row||_2, b / ||row||_2; rows with norm <= 1e-10 are dropped (h = +inf
+// tells the solver the row does not exist).
+template <int RPL>
+__device__ __forceinline__ void renormalize_rows(const WarpScratch& w, int cnt, int d, int lane, double (&h)[RPL]) {
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int i = lane + 32 * r;
+        if (i < cnt) {
+            const double* row = w.G + i;
+            const int MP = w.MP;
+            const double nrm = sqrt(np_sum_squares([&](int j) { return row[j * MP]; }, d));
+            if (nrm > 1e-10) {
+                const double mult = __ddiv_rn(1.0, nrm);
+                for (int j = 0; j < d; ++j) w.G[j * MP + i] = __dmul_rn(row[j * MP], mult);
+                h[r] = __dmul_rn(h[r], mult);
+            } else {
+                for (int j = 0; j < d; ++j) w.G[j * MP + i] = 0.0;
+                h[r] = 1e308 * 10.0;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// extra column d = ||row||_2 of the staged rows (polytope.py:1285-1286)
+template <int RPL>
+__device__ __forceinline__ void append_norm_column(const WarpScratch& w, int cnt, int d, int lane) {
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int i = lane + 32 * r;
+        if (i < cnt) {
+            const double* row = w.G + i;
+            const int MP = w.MP;
+            w.G[d * MP + i] = sqrt(np_sum_squares([&](int j) { return row[j * MP]; }, d));
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------
+// Problems
+// ------------------------------------------------------------------------
+struct GenericLP {
+    const double *G, *h, *c;
+    const int32_t* m_rows;
+    int m, nn;
+    double *x, *fun;
+    int8_t* status;
+    int32_t* iters;
+    __device__ int n() const { return nn; }
+    template <int RPL>
+    __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+        mm = m_rows ? min(max(m_rows[t], 0), m) : m;
+        stage_first_rows<RPL>(w, G + (size_t)t * m * nn, h + (size_t)t * m, mm, nn, nn, lane, hh);
+        cc = lane < nn ? c[(size_t)t * nn + lane] : 0.0;
+        return true;
+    }
+    template <int RPL>
+    __device__ void store(long long t, const WarpScratch&, int lane, const LpResult& res) const {
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        if (lane < nn) x[(size_t)t * nn + lane] = res.status == ST_OPTIMAL ? res.x : nan;
+        if (lane == 0) {
+            fun[t] = res.status == ST_OPTIMAL ? res.fun : nan;
+            status[t] = (int8_t)res.status;
+            if (iters) iters[t] = res.iters;
+        }
+    }
+};
+
+struct ChebyLP {
+    const double *A, *b;
+    const int32_t* m_rows;
+    const uint64_t* rows;     // nullable row masks
+    const uint32_t* skip_flags;  // nullable: skip polytope when (flags & skip_mask)
+    uint32_t skip_mask;
+    int m, d;
+    double *r, *xc;
+    int8_t* status;
+    __device__ int n() const { return d + 1; }
+    template <int RPL>
+    __device__ bool load(long long p, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+        if (skip_flags && (skip_flags[p] & skip_mask)) return false;
+        const double* Ap = A + (size_t)p * m * d;
+        const double* bp = b + (size_t)p * m;
+        if (rows) {
+            mm = stage_masked_rows<RPL>(w, Ap, bp, m, d, d + 1, rows[p] & low_bits(m), lane, hh);
+        } else {
+            mm = m_rows ? min(max(m_rows[p], 0), m) : m;
+            stage_first_rows<RPL>(w, Ap, bp, mm, d, d + 1, lane, hh);
+        }
+        append_norm_column<RPL>(w, mm, d, lane);
+        cc = lane == d ? -1.0 : 0.0;
+        return true;
+    }
+    template <int RPL>
+    __device__ void store(long long p, const WarpScratch&, int lane, const LpResult& res) const {
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        const double v = res.status == ST_OPTIMAL ? res.x : nan;
+        if (lane < d) xc[(size_t)p * d + lane] = v;
+        if (lane == d) r[p] = v;
+        if (lane == 0) status[p] = (int8_t)res.status;
+    }
+};
+
+struct BboxLP {
+    const double *A, *b;
+    const int32_t* m_rows;
+    const uint64_t* rows;        // nullable row masks
+    const uint32_t* need_flags;  // nullable: run only when (flags & need_mask)
+    uint32_t need_mask;
+    int m, d, renorm;
+    double *val_lo, *val_hi;     // [P][d] each: optimised coordinate of the lower / upper LP
+    int8_t* status;              // [P][2d]
+    __device__ int n() const { return d; }
+    template <int RPL>
+    __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+        const long long p = t / (2 * d);
+        const int q = (int)(t - p * 2 * d);
+        if (need_flags && !(need_flags[p] & need_mask)) return false;
+        const double* Ap = A + (size_t)p * m * d;
+        const double* bp = b + (size_t)p * m;
+        if (rows) {
+            mm = stage_masked_rows<RPL>(w, Ap, bp, m, d, d, rows[p] & low_bits(m), lane, hh);
+        } else {
+            mm = m_rows ? min(max(m_rows[p], 0), m) : m;
+            stage_first_rows<RPL>(w, Ap, bp, mm, d, d, lane, hh);
+        }
+        if (renorm) renormalize_rows<RPL>(w, mm, d, lane, hh);
+        const int i = q < d ? q : q - d;
+        cc = lane == i ? (q < d ? 1.0 : -1.0) : 0.0;
+        return true;
+    }
+    template <int RPL>
+    __device__ void store(long long t, const WarpScratch&, int lane, const LpResult& res) const {
+        const long long p = t / (2 * d);
+        const int q = (int)(t - p * 2 * d);
+        const int i = q < d ? q : q - d;
+        if (lane == i) {
+            (q < d ? val_lo : val_hi)[p * d + i] = res.status == ST_OPTIMAL ? res.x : 0.0;
+            status[t] = (int8_t)res.status;
+        }
+    }
+};
+
+// reduce()'s row loop (polytope.py:1142-1160).  Work item t = p*m + k, k-th
+// surviving row of polytope p.  h reproduces the reference's in-place
+// `h[k] += 0.1; ...; h[k] -= 0.1`: rows before k carry the one-ulp drift.
+struct RowLP {
+    const double *A, *b;        // constructor-normalised
+    const uint64_t* rows;       // surviving rows (after duplicate / bbox filters)
+    uint32_t* flags;
+    uint32_t run_mask;          // run only when (flags & run_mask)
+    int m, d;
+    double abs_tol;
+    unsigned long long* keep;   // OR-accumulated
+    __device__ int n() const { return d; }
+    template <int RPL>
+    __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+        const long long p = t / m;
+        const int k = (int)(t - p * m);
+        if (!(flags[p] & run_mask)) return false;
+        const uint64_t mask = rows[p] & low_bits(m);
+        if (k >= __popcll(mask)) return false;
+        mm = stage_masked_rows<RPL>(w, A + (size_t)p * m * d, b + (size_t)p * m, m, d, d, mask, lane, hh);
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const int i = lane + 32 * r;
+            if (i < k) hh[r] = __dadd_rn(__dadd_rn(hh[r], 0.1), -0.1);
+            else if (i == k) hh[r] = __dadd_rn(hh[r], 0.1);
+        }
+        cc = lane < d ? -w.G[lane * w.MP + k] : 0.0;
+        return true;
+    }
+    template <int RPL>
+    __device__ void store(long long t, const WarpScratch& w, int lane, const LpResult& res) const {
+        const long long p = t / m;
+        const int k = (int)(t - p * m);
+        if (lane != 0) return;
+        const uint64_t mask = rows[p] & low_bits(m);
+        const int orig = nth_set_bit(mask, k);
+        bool kept = false;
+        if (res.status == ST_OPTIMAL) {
+            const double hk = __dadd_rn(__dadd_rn(b[(size_t)p * m + orig], 0.1), -0.1);
+            kept = (-res.fun - hk) > abs_tol;
+        } else if (res.status == ST_UNBOUNDED) {
+            kept = true;
+        } else {
+            atomicOr(flags + p, PB200_F_LPFAIL);
+        }
+        if (kept) atomicOr(keep + p, 1ull << orig);
+    }
+};
+
+// is_adjacent, overlap=True (polytope.py:1856-1866): rows of both cells, b + tol,
+// constructor normalisation, Chebyshev LP, radius > tol/10.
+struct AdjacentLP {
+    const double *A, *b;
+    int ncell, mc, d;
+    const int32_t *pi, *pj;
+    double abs_tol;
+    uint8_t* adjacent;
+    double* radius;
+    int8_t* status;
+    __device__ int n() const { return d + 1; }
+    __device__ void pair(long long t, int& i, int& j) const {
+        if (pi) { i = pi[t]; j = pj[t]; return; }
+        // t = i(i-1)/2 + j, j < i
+        long long ii = (long long)((1.0 + sqrt(1.0 + 8.0 * (double)t)) * 0.5);
+        while (ii * (ii - 1) / 2 > t) --ii;
+        while ((ii + 1) * ii / 2 <= t) ++ii;
+        i = (int)ii;
+        j = (int)(t - ii * (ii - 1) / 2);
+    }
+    template <int RPL>
+    __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+        int ci, cj;
+        pair(t, ci, cj);
+        mm = 2 * mc;
+        zero_G<RPL>(w, d + 1, lane);
+        const int total = mc * d;
+        const double* A1 = A + (size_t)ci * total;
+        const double* A2 = A + (size_t)cj * total;
+        for (int e = lane; e < total; e += 32) {
+            const int i = e / d, j = e - i * d;
+            w.G[j * w.MP + i] = __ldg(A1 + e);
+            w.G[j * w.MP + mc + i] = __ldg(A2 + e);
+        }
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const int i = lane + 32 * r;
+            double v = 0.0;
+            if (i < mc) v = __dadd_rn(__ldg(b + (size_t)ci * mc + i), abs_tol);
+            else if (i < 2 * mc) v = __dadd_rn(__ldg(b + (size_t)cj * mc + i - mc), abs_tol);
+            hh[r] = v;
+        }
+        __syncwarp();
+        renormalize_rows<RPL>(w, mm, d, lane, hh);
+        append_norm_column<RPL>(w, mm, d, lane);
+        cc = lane == d ? -1.0 : 0.0;
+        return true;
+    }
+    template <int RPL>
+    __device__ void store(long long t, const WarpScratch&, int lane, const LpResult& res) const {
+        if (lane != d) return;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        const double rr = res.status == ST_OPTIMAL ? res.x : nan;
+        adjacent[t] = (res.status == ST_OPTIMAL && rr > abs_tol / 10) ? 1 : 0;
+        if (radius) radius[t] = rr;
+        if (status) status[t] = (int8_t)res.status;
+    }
+};
+
+// ------------------------------------------------------------------------
+// the one LP kernel
+// ------------------------------------------------------------------------
+template <int RPL, class Prob>
+__global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long n_items) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = prob.n();
+    const WarpScratch w = lp_carve(smem + (size_t)wib * lp_scratch_doubles(RPL, n), RPL, n);
+    const long long stride = (long long)gridDim.x * WPC;
+    for (long long t = (long long)blockIdx.x * WPC + wib; t < n_items; t += stride) {
+        int m;
+        double c;
+        double h[RPL];
+        if (!prob.template load<RPL>(t, w, lane, m, c, h)) continue;
+        const LpResult res = lp_solve_warp<RPL>(w, m, n, c, h);
+        prob.template store<RPL>(t, w, lane, res);
+        __syncwarp();
+    }
+}
+
+static int g_sm_count = 0;
+
+template <int RPL, class Prob>
+static int launch_lp_rpl(const Prob& prob, long long n_items, int n, cudaStream_t st) {
+    if (n_items <= 0) return PB200_OK;
+    const size_t smem = (size_t)WPC * lp_scratch_doubles(RPL, n) * sizeof(double);
+    if (smem > 227 * 1024) return fail(PB200_EUNSUPPORTED, "LP too large for shared memory");
+    auto kern = lp_kernel<RPL, Prob>;
+    PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!g_sm_count) {
+        int dev = 0;
+        PB_CHECK_CUDA(cudaGetDevice(&dev));
+        PB_CHECK_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int per_sm = 0;
+    PB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPC * 32, smem));
+    if (per_sm < 1) return fail(PB200_EUNSUPPORTED, "LP kernel does not fit on an SM");
+    // persistent grid: a whole number of waves (multiple of the SM count)
+    long long grid = (long long)g_sm_count * per_sm;
+    const long long need = (n_items + WPC - 1) / WPC;
+    if (need < grid) grid = need;
+    kern<<<(unsigned)grid, WPC * 32, smem, st>>>(prob, n_items);
+    ++g_launches;
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
+template <class Prob>
+static int launch_lp(const Prob& prob, long long n_items, int m, int n, cudaStream_t st) {
+    if (n < 1 || n > LP_MAX_N) return fail(PB200_EUNSUPPORTED, "number of LP columns must be in 1..32");
+    if (m < 1 || m > 128) return fail(PB200_EUNSUPPORTED, "number of LP rows must be in 1..128");
+    if (m <= 32) return launch_lp_rpl<1>(prob, n_items, n, st);
+    if (m <= 64) return launch_lp_rpl<2>(prob, n_items, n, st);
+    return launch_lp_rpl<4>(prob, n_items, n, st);
+}
+
+// ------------------------------------------------------------------------
+// small non-LP kernels of the pipelines (one warp per polytope)
+// ------------------------------------------------------------------------
+// Polytope.__init__ (polytope.py:128-138)
+__global__ void normalize_kernel(const double* __restrict__ A, const double* __restrict__ b,
+                                 const int32_t* __restrict__ m_rows, int P, int m, int d, int do_norm,
+                                 double* __restrict__ An, double* __restrict__ bn, uint64_t* __restrict__ valid) {
+    const int lane = threadIdx.x & 31;
+    const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= P) return;
+    const int mm = m_rows ? min(max(m_rows[p], 0), m) : m;
+    uint64_t mask = 0;
+    for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        bool ok = false;
+        if (i < m) {
+            const double* row = A + ((size_t)p * m + i) * d;
+            double* out = An + ((size_t)p * m + i) * d;
+            if (i < mm && !do_norm) {       // rows already normalised by a constructor
+                ok = true;
+                for (int j = 0; j < d; ++j) out[j] = row[j];
+                bn[(size_t)p * m + i] = b[(size_t)p * m + i];
+            } else if (i < mm) {
+                const double nrm = sqrt(np_sum_squares([&](int j) { return row[j]; }, d));
+                ok = nrm > 1e-10;
+                const double mult = ok ? __ddiv_rn(1.0, nrm) : 0.0;
+                for (int j = 0; j < d; ++j) out[j] = __dmul_rn(row[j], mult);
+                bn[(size_t)p * m + i] = ok ? __dmul_rn(b[(size_t)p * m + i], mult) : 0.0;
+            } else {
+                for (int j = 0; j < d; ++j) out[j] = 0.0;
+                bn[(size_t)p * m + i] = 0.0;
+            }
+        }
+        const unsigned bal = __ballot_sync(FULL_MASK, ok);
+        mask |= (uint64_t)bal << base;
+    }
+    if (lane == 0 && valid) valid[p] = mask;
+}
+
+// reduce(): is_fulldim verdict, b == inf drop and duplicate-direction filter
+// (polytope.py:1081-1116).  One warp per polytope.
+__global__ void prefilter_kernel(const double* __restrict__ An, const double* __restrict__ bn,
+                                 const uint64_t* __restrict__ valid, const double* __restrict__ r,
+                                 const int8_t* __restrict__ cheb_status, int P, int m, int d, double abs_tol,
+                                 uint64_t* __restrict__ rows1, uint32_t* __restrict__ flags) {
+    extern __shared__ double sh[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (p >= P) return;
+    double* an = sh + (size_t)wib * (m * d + 2 * m);   // a_normed [m][d]
+    double* bs = an + m * d;                           // b * a_norm
+    const double* Ap = An + (size_t)p * m * d;
+    const double* bp = bn + (size_t)p * m;
+    // ABS_TOL of is_fulldim's default argument, polytope.py:962 (not reduce's abs_tol)
+    const bool fulldim = cheb_status[p] == ST_OPTIMAL && r[p] > 1e-7;
+    if (!fulldim) {
+        if (lane == 0) { rows1[p] = 0; flags[p] = PB200_F_EMPTY; }
+        return;
+    }
+    uint64_t alive = valid[p] & low_bits(m);
+    for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        bool fin = false;
+        if (i < m && ((alive >> i) & 1ull)) {
+            const double bi = bp[i];
+            fin = bi != __longlong_as_double(0x7ff0000000000000ll);
+            const double* row = Ap + (size_t)i * d;
+            const double an_i = __ddiv_rn(1.0, sqrt(np_sum_squares([&](int j) { return row[j]; }, d)));
+            for (int j = 0; j < d; ++j) an[i * d + j] = __dmul_rn(row[j], an_i);
+            bs[i] = __dmul_rn(bi, an_i);
+        }
+        const unsigned bal = __ballot_sync(FULL_MASK, fin);
+        alive = (alive & ~((uint64_t)0xffffffffu << base)) | ((uint64_t)bal << base);
+    }
+    __syncwarp();
+    // all pairs i < j of alive rows; the removed set is a union, order-free
+    unsigned rem_lo = 0, rem_hi = 0;
+    for (int i = 0; i < m; ++i) {
+        if (!((alive >> i) & 1ull)) continue;
+        for (int j = i + 1 + lane; j < m; j += 32) {
+            if (!((alive >> j) & 1ull)) continue;
+            double dot = 0.0;
+            for (int q = 0; q < d; ++q) dot = fma(an[i * d + q], an[j * d + q], dot);
+            if (dot > 1.0 - abs_tol) {
+                const int rm = bs[i] < bs[j] ? j : i;
+                if (rm < 32) rem_lo |= 1u << rm; else rem_hi |= 1u << (rm - 32);
+            }
+        }
+    }
+    rem_lo = __reduce_or_sync(FULL_MASK, rem_lo);
+    rem_hi = __reduce_or_sync(FULL_MASK, rem_hi);
+    const uint64_t keep = alive & ~(((uint64_t)rem_hi << 32) | rem_lo);
+    if (lane == 0) {
+        rows1[p] = keep;
+        flags[p] = 0;
+    }
+}
+
+// pipeline control bits kept in the upper half of flags[] while reduce runs
+constexpr uint32_t CTL_NEED_BBOX = 1u << 16;
+constexpr uint32_t CTL_ROW_LOOP = 1u << 17;
+constexpr uint32_t CTL_MASK = 0xffff0000u;
+
+// decide early exit / bbox need after the duplicate filter (polytope.py:1113-1118)
+__global__ void plan_kernel(const uint64_t* __restrict__ rows1, uint32_t* __restrict__ flags, int P, int d) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    uint32_t f = flags[p];
+    if (f & PB200_F_EMPTY) return;
+    const int neq = __popcll(rows1[p]);
+    if (neq <= d + 1) { flags[p] = f; return; }              // early exit, minrep stays False
+    if (neq > 3 * d) f |= CTL_NEED_BBOX | PB200_F_BBOX;
+    else f |= CTL_ROW_LOOP;
+    flags[p] = f;
+}
+
+// bounding-box candidate filter (polytope.py:1119-1138). One warp per polytope.
+__global__ void candidate_kernel(const double* __restrict__ An, const double* __restrict__ bn,
+                                 const uint64_t* __restrict__ rows1, const double* __restrict__ bblo,
+                                 const double* __restrict__ bbhi, const int8_t* __restrict__ bbstatus, int P, int m, int d,
+                                 uint64_t* __restrict__ rows2, uint32_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= P) return;
+    const uint32_t f = flags[p];
+    const uint64_t mask1 = rows1[p];
+    if (!(f & CTL_NEED_BBOX)) {
+        if (lane == 0) rows2[p] = mask1;
+        return;
+    }
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    uint64_t cand = 0;
+    bool lpfail = false;
+    for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        bool c = false;
+        if (i < m && ((mask1 >> i) & 1ull)) {
+            const double* row = An + ((size_t)p * m + i) * d;
+            double t1 = 0.0, t2 = 0.0;
+            for (int j = 0; j < d; ++j) {
+                const int8_t sl = bbstatus[(size_t)p * 2 * d + j], su = bbstatus[(size_t)p * 2 * d + d + j];
+                double lo = bblo[(size_t)p * d + j], hi = bbhi[(size_t)p * d + j];
+                if (sl == ST_UNBOUNDED) lo = -inf; else if (sl == ST_INFEASIBLE) lo = 0.0; else if (sl != ST_OPTIMAL) lpfail = true;
+                if (su == ST_UNBOUNDED) hi = inf; else if (su == ST_INFEASIBLE) hi = lo; else if (su != ST_OPTIMAL) lpfail = true;
+                const double a = row[j];
+                const double ap = a > 0.0 ? a : __dmul_rn(0.0, a);
+                t1 = __dadd_rn(t1, __dmul_rn(ap, __dadd_rn(hi, -lo)));
+                t2 = __dadd_rn(t2, __dmul_rn(a, lo));
+            }
+            const double v = t1 - (bn[(size_t)p * m + i] - t2);
+            c = !(v < -1e-4);
+        }
+        const unsigned bal = __ballot_sync(FULL_MASK, c);
+        cand |= (uint64_t)bal << base;
+    }
+    lpfail = __any_sync(FULL_MASK, lpfail);
+    if (lane == 0) {
+        const uint64_t mask2 = mask1 & cand;
+        rows2[p] = mask2;
+        uint32_t g = f & ~CTL_NEED_BBOX;
+        if (lpfail) g |= PB200_F_LPFAIL;
+        if (__popcll(mask2) > d + 1) g |= CTL_ROW_LOOP;
+        flags[p] = g;
+    }
+}
+
+// assemble keep masks, drifted b, LP counts and public flags
+__global__ void finalize_kernel(const double* __restrict__ bn, const uint64_t* __restrict__ rows2,
+                                const unsigned long long* __restrict__ keep_lp, uint32_t* __restrict__ flags,
+                                int P, int m, int d, uint64_t* __restrict__ keep, double* __restrict__ b_out,
+                                int32_t* __restrict__ n_lp) {
+    const int lane = threadIdx.x & 31;
+    const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= P) return;
+    const uint32_t f = flags[p];
+    const uint64_t mask2 = rows2[p];
+    const bool looped = f & CTL_ROW_LOOP;
+    for (int i = lane; i < m; i += 32) {
+        double v = bn[(size_t)p * m + i];
+        if (looped && ((mask2 >> i) & 1ull)) v = __dadd_rn(__dadd_rn(v, 0.1), -0.1);
+        b_out[(size_t)p * m + i] = v;
+    }
+    if (lane == 0) {
+        uint32_t g = f & ~CTL_MASK;
+        uint64_t k = 0;
+        int lps = 1;
+        if (!(f & PB200_F_EMPTY)) {
+            if (f & PB200_F_BBOX) lps += 2 * d;
+            if (looped) { k = keep_lp[p]; lps += __popcll(mask2); g |= PB200_F_MINREP; }
+            else k = mask2;
+        }
+        keep[p] = k;
+        flags[p] = g;
+        if (n_lp) n_lp[p] = lps;
+    }
+}
+
+// bounding_box status conventions (polytope.py:1372-1402)
+__global__ void bbox_resolve_kernel(const int8_t* __restrict__ status, int P, int d, double* lo, double* hi) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)P * d) return;
+    const long long p = t / d;
+    const int j = (int)(t - p * d);
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const int8_t sl = status[p * 2 * d + j], su = status[p * 2 * d + d + j];
+    double l = lo[t], u = hi[t];
+    if (sl == ST_UNBOUNDED) l = -inf; else if (sl == ST_INFEASIBLE) l = 0.0; else if (sl != ST_OPTIMAL) l = nan;
+    if (su == ST_UNBOUNDED) u = inf; else if (su == ST_INFEASIBLE) u = l; else if (su != ST_OPTIMAL) u = nan;
+    lo[t] = l;
+    hi[t] = u;
+}
+
+static inline unsigned blocks_for(long long threads, int block) { return (unsigned)((threads + block - 1) / block); }
+
+struct ReduceWorkspace {
+    double *An, *bn, *bblo, *bbhi;
+    uint64_t *valid, *rows1, *rows2;
+    unsigned long long* keep_lp;
+    int8_t *cheb_status, *bbstatus;
+    size_t bytes;
+};
+static ReduceWorkspace carve_reduce(void* base, int P, int m, int d) {
+    ReduceWorkspace w;
+    char* p = (char*)base;
+    auto take = [&](size_t n) { char* q = p; p += (n + 255) & ~(size_t)255; return q; };
+    w.An = (double*)take(sizeof(double) * P * m * d);
+    w.bn = (double*)take(sizeof(double) * P * m);
+    w.bblo = (double*)take(sizeof(double) * P * d);
+    w.bbhi = (double*)take(sizeof(double) * P * d);
+    w.valid = (uint64_t*)take(sizeof(uint64_t) * P);
+    w.rows1 = (uint64_t*)take(sizeof(uint64_t) * P);
+    w.rows2 = (uint64_t*)take(sizeof(uint64_t) * P);
+    w.keep_lp = (unsigned long long*)take(sizeof(uint64_t) * P);
+    w.cheb_status = (int8_t*)take(P);
+    w.bbstatus = (int8_t*)take((size_t)P * 2 * d);
+    w.bytes = (size_t)(p - (char*)base);
+    return w;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" {
+
+const char* pb200_version(void) { return "polytope_b200 0.1 (sm_100a)"; }
+const char* pb200_last_error(void) { return g_err; }
+long long pb200_launch_count(void) { return g_launches; }
+
+int pb200_lp_batch(const double* G, const double* h, const double* c, const int32_t* m_rows, int B, int m, int n,
+                   double* x, double* fun, int8_t* status, int32_t* iters, void* stream) {
+    if (B < 0 || !G || !h || !c || !x || !fun || !status) return fail(PB200_EINVAL, "pb200_lp_batch: null pointer or negative batch");
+    GenericLP prob{G, h, c, m_rows, m, n, x, fun, status, iters};
+    return launch_lp(prob, B, m, n, (cudaStream_t)stream);
+}
+
+int pb200_normalize_batch(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, double* An,
+                          double* bn, uint64_t* valid, void* stream) {
+    if (P < 0 || !A || !b || !An || !bn) return fail(PB200_EINVAL, "pb200_normalize_batch: null pointer");
+    if (m < 1 || m > 64 || d < 1 || d > 128) return fail(PB200_EUNSUPPORTED, "normalize: need 1<=m<=64, 1<=d<=128");
+    if (P == 0) return PB200_OK;
+    normalize_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, (cudaStream_t)stream>>>(A, b, m_rows, P, m, d, 1, An, bn, valid);
+    ++g_launches;
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
+int pb200_cheby_batch(const double* A, const double* b, const int32_t* m_rows, const uint64_t* rows, int P, int m,
+                      int d, double* r, double* xc, int8_t* status, void* stream) {
+    if (P < 0 || !A || !b || !r || !xc || !status) return fail(PB200_EINVAL, "pb200_cheby_batch: null pointer");
+    if (rows && m > 64) return fail(PB200_EUNSUPPORTED, "row masks need m <= 64");
+    ChebyLP prob{A, b, m_rows, rows, nullptr, 0, m, d, r, xc, status};
+    return launch_lp(prob, P, m, d + 1, (cudaStream_t)stream);
+}
+
+int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, double* lo,
+                     double* hi, int8_t* status, void* stream) {
+    if (P < 0 || !A || !b || !lo || !hi || !status) return fail(PB200_EINVAL, "pb200_bbox_batch: null pointer");
+    if (d < 1 || d > LP_MAX_N) return fail(PB200_EUNSUPPORTED, "bbox: need 1 <= d <= 32");
+    if (P == 0) return PB200_OK;
+    // the LP kernel writes the raw optimised coordinates into lo / hi, the
+    // resolve kernel then applies the reference's status conventions in place
+    BboxLP prob{A, b, m_rows, nullptr, nullptr, 0, m, d, 0, lo, hi, status};
+    int rc = launch_lp(prob, (long long)P * 2 * d, m, d, (cudaStream_t)stream);
+    if (rc) return rc;
+    bbox_resolve_kernel<<<blocks_for((long long)P * d, 256), 256, 0, (cudaStream_t)stream>>>(status, P, d, lo, hi);
+    ++g_launches;
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
+size_t pb200_reduce_workspace_bytes(int P, int m, int d) {
+    if (P < 0 || m < 1 || d < 1) return 0;
+    return carve_reduce(nullptr, P, m, d).bytes;
+}
+
+int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, double abs_tol,
+                       int normalize, uint64_t* keep, uint32_t* flags, double* r, double* xc, double* b_out, double* A_out,
+                       int32_t* n_lp, void* workspace, size_t workspace_bytes, void* stream) {
+    if (P < 0 || !A || !b || !keep || !flags || !r || !xc || !b_out || !workspace)
+        return fail(PB200_EINVAL, "pb200_reduce_batch: null pointer");
+    if (m < 1 || m > 64) return fail(PB200_EUNSUPPORTED, "reduce: need 1 <= m <= 64 rows (row sets are 64-bit masks)");
+    if (d < 1 || d + 1 > LP_MAX_N) return fail(PB200_EUNSUPPORTED, "reduce: need 1 <= d <= 31");
+    if (P == 0) return PB200_OK;
+    ReduceWorkspace ws = carve_reduce(workspace, P, m, d);
+    if (ws.bytes > workspace_bytes) return fail(PB200_EWORKSPACE, "pb200_reduce_batch: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* An = A_out ? A_out : ws.An;
+    int rc;
+    // 1. constructor normalisation
+    normalize_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(A, b, m_rows, P, m, d, normalize ? 1 : 0, An, ws.bn,
+                                                                       ws.valid);
+    ++g_launches;
+    PB_CHECK_CUDA(cudaGetLastError());
+    // 2. is_fulldim: one Chebyshev LP per polytope
+    ChebyLP cheb{An, ws.bn, nullptr, ws.valid, nullptr, 0, m, d, r, xc, ws.cheb_status};
+    if ((rc = launch_lp(cheb, P, m, d + 1, st))) return rc;
+    // 3. b == inf drop + duplicate-direction filter, then plan
+    {
+        const int wpb = 4;
+        const size_t sh = (size_t)wpb * (m * d + 2 * m) * sizeof(double);
+        prefilter_kernel<<<blocks_for(P, wpb), wpb * 32, sh, st>>>(An, ws.bn, ws.valid, r, ws.cheb_status, P, m, d,
+                                                                 abs_tol, ws.rows1, flags);
+        ++g_launches;
+        PB_CHECK_CUDA(cudaGetLastError());
+        plan_kernel<<<blocks_for(P, 256), 256, 0, st>>>(ws.rows1, flags, P, d);
+        ++g_launches;
+        PB_CHECK_CUDA(cudaGetLastError());
+    }
+    // 4. bounding box of Polytope(A_arr, b_arr) where neq > 3 nx
+    BboxLP bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus};
+    if ((rc = launch_lp(bb, (long long)P * 2 * d, m, d, st))) return rc;
+    // 5. candidate filter
+    candidate_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(An, ws.bn, ws.rows1, ws.bblo, ws.bbhi, ws.bbstatus,
+                                                                       P, m, d, ws.rows2, flags);
+    ++g_launches;
+    PB_CHECK_CUDA(cudaGetLastError());
+    // 6. one LP per surviving row
+    PB_CHECK_CUDA(cudaMemsetAsync(ws.keep_lp, 0, sizeof(uint64_t) * P, st));
+    RowLP row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, m, d, abs_tol, ws.keep_lp};
+    if ((rc = launch_lp(row, (long long)P * m, m, d, st))) return rc;
+    // 7. results
+    finalize_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(ws.bn, ws.rows2, ws.keep_lp, flags, P, m, d, keep,
+                                                                      b_out, n_lp);
+    ++g_launches;
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
+int pb200_adjacent_pairs(const double* A, const double* b, int ncell, int mc, int d, const int32_t* pair_i,
+                         const int32_t* pair_j, long long T, double abs_tol, uint8_t* adjacent, double* radius,
+                         int8_t* status, void* stream) {
+    if (!A || !b || !adjacent || T < 0 || ncell < 0) return fail(PB200_EINVAL, "pb200_adjacent_pairs: bad argument");
+    if ((pair_i == nullptr) != (pair_j == nullptr)) return fail(PB200_EINVAL, "pair_i and pair_j must both be given or both NULL");
+    if (!pair_i && T != (long long)ncell * (ncell - 1) / 2)
+        return fail(PB200_EINVAL, "implicit pair enumeration needs T == ncell*(ncell-1)/2");
+    if (2 * mc > 64) return fail(PB200_EUNSUPPORTED, "adjacent: need 2*mc <= 64 rows");
+    AdjacentLP prob{A, b, ncell, mc, d, pair_i, pair_j, abs_tol, adjacent, radius, status};
+    return launch_lp(prob, T, 2 * mc, d + 1, (cudaStream_t)stream);
+}
+
+}  // extern "C"

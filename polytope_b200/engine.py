@@ -1,0 +1,205 @@
+"""Batched device operations of the LP hot path (host side of the C ABI).
+
+Every function takes either torch CUDA float64 tensors (results stay on the
+device, nothing synchronises) or numpy arrays / CPU tensors (inputs are copied
+to the device on the current CUDA stream, results come back as numpy arrays).
+torch is plumbing only: device memory, streams.  All arithmetic happens in
+libpolytope_b200.so; there is no fallback.
+"""
+import numpy as np
+import torch
+
+from polytope_b200 import _capi
+
+F_EMPTY, F_MINREP, F_BBOX, F_LPFAIL = 1, 2, 4, 8
+ABS_TOL = 1e-7          # polytope/polytope.py:83
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _capi.Pb200Error(
+            'polytope_b200 needs a CUDA device (B200, sm_100a); none is visible '
+            'and there is no CPU fallback')
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(x, dtype=torch.float64):
+    """-> (contiguous CUDA tensor, was_host)."""
+    if isinstance(x, torch.Tensor):
+        host = not x.is_cuda
+        t = x.to(device='cuda', dtype=dtype, non_blocking=True) if host or x.dtype != dtype else x
+        return t.contiguous(), host
+    a = np.ascontiguousarray(x, dtype={torch.float64: np.float64, torch.int32: np.int32,
+                                       torch.int64: np.int64}[dtype])
+    return torch.from_numpy(a).to('cuda', non_blocking=True), True
+
+
+def _opt(x, dtype):
+    if x is None:
+        return None, 0
+    t, _ = _dev(x, dtype)
+    return t, t.data_ptr()
+
+
+def _out(host, *tensors):
+    if not host:
+        return tensors
+    return tuple(t.cpu().numpy() for t in tensors)
+
+
+def lp_batch(C, G, H, m_rows=None):
+    """B independent LPs min c'x s.t. Gx <= h (solvers.lpsolve, one per row of the batch).
+
+    C[B,n], G[B,m,n], H[B,m] -> status[B] int8, X[B,n], fun[B], iters[B] int32.
+    """
+    _require_cuda()
+    lib = _capi.lib()
+    G, host = _dev(G)
+    C, _ = _dev(C)
+    H, _ = _dev(H)
+    B, m, n = G.shape
+    assert C.shape == (B, n) and H.shape == (B, m), (C.shape, G.shape, H.shape)
+    mr, mr_ptr = _opt(m_rows, torch.int32)
+    X = torch.empty((B, n), dtype=torch.float64, device='cuda')
+    fun = torch.empty(B, dtype=torch.float64, device='cuda')
+    status = torch.empty(B, dtype=torch.int8, device='cuda')
+    iters = torch.empty(B, dtype=torch.int32, device='cuda')
+    _capi.check(lib.pb200_lp_batch(G.data_ptr(), H.data_ptr(), C.data_ptr(), mr_ptr, B, m, n,
+                                   X.data_ptr(), fun.data_ptr(), status.data_ptr(),
+                                   iters.data_ptr(), _stream()), 'pb200_lp_batch')
+    return _out(host, status, X, fun, iters)
+
+
+def normalize_batch(A, b, m_rows=None):
+    """Polytope.__init__ row normalisation for stacked polytopes -> (An, bn, valid u64 mask)."""
+    _require_cuda()
+    lib = _capi.lib()
+    A, host = _dev(A)
+    b, _ = _dev(b)
+    P, m, d = A.shape
+    mr, mr_ptr = _opt(m_rows, torch.int32)
+    An = torch.empty_like(A)
+    bn = torch.empty_like(b)
+    valid = torch.empty(P, dtype=torch.int64, device='cuda')
+    _capi.check(lib.pb200_normalize_batch(A.data_ptr(), b.data_ptr(), mr_ptr, P, m, d,
+                                          An.data_ptr(), bn.data_ptr(), valid.data_ptr(),
+                                          _stream()), 'pb200_normalize_batch')
+    return _out(host, An, bn, valid)
+
+
+def cheby_batch(A, b, m_rows=None, rows=None):
+    """Chebyshev LP of each polytope, rows used as given -> (r, xc, status)."""
+    _require_cuda()
+    lib = _capi.lib()
+    A, host = _dev(A)
+    b, _ = _dev(b)
+    P, m, d = A.shape
+    mr, mr_ptr = _opt(m_rows, torch.int32)
+    rw, rw_ptr = _opt(rows, torch.int64)
+    r = torch.empty(P, dtype=torch.float64, device='cuda')
+    xc = torch.empty((P, d), dtype=torch.float64, device='cuda')
+    status = torch.empty(P, dtype=torch.int8, device='cuda')
+    _capi.check(lib.pb200_cheby_batch(A.data_ptr(), b.data_ptr(), mr_ptr, rw_ptr, P, m, d,
+                                      r.data_ptr(), xc.data_ptr(), status.data_ptr(),
+                                      _stream()), 'pb200_cheby_batch')
+    return _out(host, r, xc, status)
+
+
+def bbox_batch(A, b, m_rows=None):
+    """bounding_box of each polytope -> (lo[P,d], hi[P,d], status[P,2d])."""
+    _require_cuda()
+    lib = _capi.lib()
+    A, host = _dev(A)
+    b, _ = _dev(b)
+    P, m, d = A.shape
+    mr, mr_ptr = _opt(m_rows, torch.int32)
+    lo = torch.empty((P, d), dtype=torch.float64, device='cuda')
+    hi = torch.empty((P, d), dtype=torch.float64, device='cuda')
+    status = torch.empty((P, 2 * d), dtype=torch.int8, device='cuda')
+    _capi.check(lib.pb200_bbox_batch(A.data_ptr(), b.data_ptr(), mr_ptr, P, m, d,
+                                     lo.data_ptr(), hi.data_ptr(), status.data_ptr(),
+                                     _stream()), 'pb200_bbox_batch')
+    return _out(host, lo, hi, status)
+
+
+class ReduceResult(object):
+    """Outputs of reduce_batch (tensors or numpy arrays, see module docstring).
+
+    keep   int64[P]   bit i set iff input row i is kept (view as uint64)
+    flags  int32[P]   F_EMPTY | F_MINREP | F_BBOX | F_LPFAIL
+    r, xc             Chebyshev ball of each input polytope
+    A, b              constructor-normalised rows; b carries the reference's drift
+    n_lp   int32[P]   LPs the reference algorithm needs for this polytope
+    """
+    __slots__ = ('keep', 'flags', 'r', 'xc', 'A', 'b', 'n_lp')
+
+    def keep_lists(self):
+        keep = np.asarray(self.keep.cpu() if isinstance(self.keep, torch.Tensor) else self.keep)
+        m = self.b.shape[1]
+        bits = (keep.astype(np.uint64)[:, None] >> np.arange(m, dtype=np.uint64)) & np.uint64(1)
+        return [np.nonzero(row)[0].tolist() for row in bits]
+
+
+def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True):
+    """reduce(Polytope(A[p], b[p])) for every p (polytope.py:1053-1163).
+
+    normalize=False reproduces reduce(poly) on rows that a constructor already
+    normalised (poly.A, poly.b are used as they are).
+    """
+    _require_cuda()
+    lib = _capi.lib()
+    A, host = _dev(A)
+    b, _ = _dev(b)
+    P, m, d = A.shape
+    mr, mr_ptr = _opt(m_rows, torch.int32)
+    res = ReduceResult()
+    keep = torch.empty(P, dtype=torch.int64, device='cuda')
+    flags = torch.empty(P, dtype=torch.int32, device='cuda')
+    r = torch.empty(P, dtype=torch.float64, device='cuda')
+    xc = torch.empty((P, d), dtype=torch.float64, device='cuda')
+    b_out = torch.empty((P, m), dtype=torch.float64, device='cuda')
+    A_out = torch.empty((P, m, d), dtype=torch.float64, device='cuda') if want_A else None
+    n_lp = torch.empty(P, dtype=torch.int32, device='cuda')
+    ws_bytes = lib.pb200_reduce_workspace_bytes(P, m, d)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device='cuda')
+    _capi.check(lib.pb200_reduce_batch(
+        A.data_ptr(), b.data_ptr(), mr_ptr, P, m, d, float(abs_tol), int(bool(normalize)),
+        keep.data_ptr(), flags.data_ptr(), r.data_ptr(), xc.data_ptr(), b_out.data_ptr(),
+        A_out.data_ptr() if want_A else 0, n_lp.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+        'pb200_reduce_batch')
+    outs = [keep, flags, r, xc, b_out, n_lp] + ([A_out] if want_A else [])
+    outs = _out(host, *outs)
+    res.keep, res.flags, res.r, res.xc, res.b, res.n_lp = outs[:6]
+    res.A = outs[6] if want_A else None
+    return res
+
+
+def adjacent_pairs(A, b, pair_i=None, pair_j=None, abs_tol=ABS_TOL):
+    """is_adjacent(cell_i, cell_j) for a list of pairs (polytope.py:1856-1866).
+
+    A[ncell,mc,d], b[ncell,mc] are constructor-normalised cells.  With no pair
+    list, all pairs j < i in find_adjacent_regions order (prop2partition.py:57-61).
+    -> (adjacent uint8[T], radius[T], status int8[T])
+    """
+    _require_cuda()
+    lib = _capi.lib()
+    A, host = _dev(A)
+    b, _ = _dev(b)
+    ncell, mc, d = A.shape
+    pi, pi_ptr = _opt(pair_i, torch.int32)
+    pj, pj_ptr = _opt(pair_j, torch.int32)
+    T = ncell * (ncell - 1) // 2 if pi is None else int(pi.numel())
+    adj = torch.empty(T, dtype=torch.uint8, device='cuda')
+    rad = torch.empty(T, dtype=torch.float64, device='cuda')
+    status = torch.empty(T, dtype=torch.int8, device='cuda')
+    _capi.check(lib.pb200_adjacent_pairs(A.data_ptr(), b.data_ptr(), ncell, mc, d, pi_ptr, pj_ptr,
+                                         T, float(abs_tol), adj.data_ptr(), rad.data_ptr(),
+                                         status.data_ptr(), _stream()), 'pb200_adjacent_pairs')
+    return _out(host, adj, rad, status)
+
+
+def launch_count():
+    return int(_capi.lib().pb200_launch_count())

@@ -1,0 +1,478 @@
+"""`Polytope` / `Region` shell and the LP-backed set operations of the hot path.
+
+Host-side mirror of the part of /root/reference/polytope/polytope.py that
+SURVEY.md section 8(a) puts on the hot path: the constructor normalisation and
+caches, `is_empty`, `is_fulldim`, `cheby_ball`, `bounding_box`, `reduce`,
+`Polytope.intersect`, `is_adjacent`.  Names, argument meaning, caching side
+effects and error behaviour follow the reference; every LP goes to the sm_100a
+kernels through `polytope_b200.engine` (no scipy, no CPU fallback).
+
+Each single-object function has a batched sibling (`*_batch`) that runs the
+whole list in a handful of kernel launches -- that is the form the throughput
+numbers are quoted on.  Operations outside the hot path (union, diff, volume,
+projection, extreme, plotting) are not provided.
+"""
+import logging
+
+import numpy as np
+
+from polytope_b200 import engine
+from polytope_b200.solvers import lpsolve  # noqa: F401  (bound at import, as polytope.py:69)
+
+logger = logging.getLogger(__name__)
+
+np.set_printoptions(precision=5, suppress=True)   # polytope.py:78, pinned by test_polytope_str
+
+ABS_TOL = 1e-7                                     # polytope.py:83
+
+
+class Polytope(object):
+    """Convex polytope {x : A x <= b} in half-space representation.
+
+    Same constructor contract as the reference (polytope.py:122-148): arrays are
+    cast to float, and unless `normalize=False` every row is scaled to unit
+    2-norm and rows with norm <= 1e-10 are dropped.
+    """
+
+    def __init__(self, A=np.array([]), b=np.array([]), minrep=False, chebR=0, chebX=None,
+                 fulldim=None, volume=None, vertices=None, normalize=True):
+        self.A = A.astype(float)
+        self.b = b.astype(float).flatten()
+        if A.size > 0 and normalize:
+            norms = np.sqrt(np.sum(A * A, 1)).flatten()
+            pos = np.nonzero(norms > 1e-10)[0]
+            mult = 1 / norms[pos]
+            self.A = self.A[pos, :] * mult[:, np.newaxis]
+            self.b = self.b[pos] * mult
+        self.minrep = minrep
+        self._chebXc = chebX
+        self._chebR = chebR
+        self.bbox = None
+        self.fulldim = fulldim
+        self._volume = None if volume is None else float(volume)
+        self.vertices = vertices
+
+    def __str__(self):
+        A_rows = str(self.A).split('\n')
+        b_rows = str(self.b.reshape(self.b.shape[0], 1)).split('\n')
+        n = len(A_rows)
+        mid = int((n - 1) / 2)
+        sep = [' |    '] * mid + [' x <= '] + [' |    '] * (n - mid - 2) + (['|    '] if n > 1 else [])
+        lines = [A_rows[k] + sep[k] + b_rows[k] for k in range(n)]
+        return 'Single polytope \n  {lines}\n'.format(lines='\n  '.join(lines))
+
+    def __len__(self):
+        return 0
+
+    def __copy__(self):
+        P = Polytope(self.A.copy(), self.b.copy())
+        P._chebXc, P._chebR = self._chebXc, self._chebR
+        P.minrep, P.bbox, P.fulldim = self.minrep, self.bbox, self.fulldim
+        return P
+
+    copy = __copy__
+
+    def __contains__(self, point):
+        point = np.asarray(point)
+        return np.all(self.A.dot(point.flatten()) - self.b < ABS_TOL)
+
+    def contains(self, points, abs_tol=ABS_TOL):
+        """Boolean array: which column vectors of `points` satisfy A x - b < abs_tol."""
+        return np.all(self.A.dot(points) - self.b[:, np.newaxis] < abs_tol, axis=0)
+
+    def intersect(self, other, abs_tol=ABS_TOL):
+        """Intersection with another Polytope (polytope.py:255-275)."""
+        if not isinstance(other, Polytope):
+            raise Exception('Polytope intersection defined only with other Polytope. '
+                            'Got instead: ' + str(type(other)))
+        if (not is_fulldim(self)) or (not is_fulldim(other)):
+            return Polytope()
+        if self.dim != other.dim:
+            raise Exception("polytopes have different dimension")
+        iA = np.vstack([self.A, other.A])
+        ib = np.hstack([self.b, other.b])
+        return reduce(Polytope(iA, ib), abs_tol=abs_tol)
+
+    @classmethod
+    def from_box(cls, intervals=[]):
+        """Hyperrectangle from [[x0_min, x0_max], ...] (polytope.py:311-354)."""
+        if not isinstance(intervals, np.ndarray):
+            try:
+                intervals = np.array(intervals)
+            except Exception:
+                raise Exception('Polytope.from_box:intervals must be a numpy ndarray or '
+                                'convertible as arg to numpy.array')
+        if intervals.ndim != 2:
+            raise Exception('Polytope.from_box: intervals must be 2 dimensional')
+        if intervals.shape[1] != 2:
+            raise Exception('Polytope.from_box: intervals must have 2 columns')
+        if (intervals[:, 0] > intervals[:, 1]).any():
+            raise Exception('Polytope.from_box: Invalid interval in from_box method.\n'
+                            'First element of an interval must not be larger than the second.')
+        n = intervals.shape[0]
+        A = np.vstack([np.eye(n), -np.eye(n)])
+        b = np.hstack([intervals[:, 1], -intervals[:, 0]])
+        return cls(A, b, minrep=True)
+
+    def scale(self, factor):
+        self.b = factor * self.b
+
+    @property
+    def dim(self):
+        try:
+            return np.shape(self.A)[1]
+        except Exception:
+            return 0.0
+
+    @property
+    def chebR(self):
+        cheby_ball(self)
+        return self._chebR
+
+    @property
+    def chebXc(self):
+        cheby_ball(self)
+        return self._chebXc
+
+    @property
+    def cheby(self):
+        return cheby_ball(self)
+
+    @property
+    def bounding_box(self):
+        if self.bbox is None:
+            self.bbox = bounding_box(self)
+        return self.bbox
+
+
+class Region(object):
+    """Possibly non-convex set: a list of Polytopes plus `props` (polytope.py:650-703)."""
+
+    def __init__(self, list_poly=None, props=None):
+        if list_poly is None:
+            list_poly = []
+        if props is None:
+            props = set()
+        if isinstance(list_poly, str):
+            self.list_poly = list_poly
+            self.props = set(props)
+            return
+        if isinstance(list_poly, Region):
+            dim = list_poly[0].dim
+            for poly in list_poly:
+                if poly.dim != dim:
+                    raise Exception("Region error: Polytopes must be of same dimension!")
+        self.list_poly = [p for p in list_poly if not is_empty(p)]
+        self.props = set(props)
+        self.bbox = None
+        self.fulldim = None
+        self._volume = None
+        self._chebXc = None
+        self._chebR = None
+
+    def __iter__(self):
+        return iter(self.list_poly)
+
+    def __getitem__(self, key):
+        return self.list_poly[key]
+
+    def __len__(self):
+        return len(self.list_poly)
+
+    def __contains__(self, point):
+        point = np.asarray(point)
+        return any(point in u for u in self.list_poly)
+
+    def contains(self, points, abs_tol=ABS_TOL):
+        points = np.asarray(points)
+        if points.shape[0] != self.dim:
+            raise ValueError('points should be column vectors')
+        contained = np.full(points.shape[1], False, dtype=bool)
+        for poly in self.list_poly:
+            contained = np.logical_or(poly.contains(points, abs_tol), contained)
+        return contained
+
+    def __copy__(self):
+        return Region(list_poly=self.list_poly[:], props=self.props.copy())
+
+    copy = __copy__
+
+    @property
+    def dim(self):
+        return np.shape(self.list_poly[0].A)[1]
+
+    @property
+    def chebR(self):
+        cheby_ball(self)
+        return self._chebR
+
+    @property
+    def chebXc(self):
+        cheby_ball(self)
+        return self._chebXc
+
+    @property
+    def cheby(self):
+        return cheby_ball(self)
+
+    @property
+    def bounding_box(self):
+        if self.bbox is None:
+            self.bbox = bounding_box(self)
+        return self.bbox
+
+
+def box2poly(box):
+    """Hyperrectangle Polytope from [[x0_min, x0_max], ...] (polytope.py:2285-2298)."""
+    return Polytope.from_box(box)
+
+
+def is_empty(polyreg):
+    """Structural emptiness, no LP (polytope.py:939-959)."""
+    n = len(polyreg)
+    if n == 0:
+        try:
+            return len(polyreg.A) == 0
+        except Exception:
+            return True
+    return bool(np.all([is_empty(p) for p in polyreg.list_poly]))
+
+
+# ---------------------------------------------------------------------------
+# batching helpers
+# ---------------------------------------------------------------------------
+def _stack(polys):
+    """Pad a list of same-dimension polytopes to one (A[P,m,d], b[P,m], m_rows[P])."""
+    d = polys[0].A.shape[1]
+    rows = np.array([p.A.shape[0] for p in polys], dtype=np.int32)
+    m = max(int(rows.max()), 1)
+    A = np.zeros((len(polys), m, d))
+    b = np.zeros((len(polys), m))
+    for k, p in enumerate(polys):
+        if p.A.shape[1] != d:
+            raise Exception("polytopes have different dimension")
+        A[k, :rows[k]] = p.A
+        b[k, :rows[k]] = p.b
+    return A, b, rows
+
+
+def _store_cheby(poly, status, r, xc):
+    """Caching side effects of cheby_ball (polytope.py:1289-1300)."""
+    if status == 0 and not r < 0:
+        poly._chebXc = np.array(xc)
+        poly._chebR = np.double(r)
+        return poly._chebR, poly._chebXc
+    return 0, None
+
+
+def cheby_ball_batch(polys):
+    """[cheby_ball(p) for p in polys] with one kernel launch for the uncached ones."""
+    out = [None] * len(polys)
+    todo = []
+    for k, p in enumerate(polys):
+        if (p._chebXc is not None) and (p._chebR is not None):
+            out[k] = (p._chebR, p._chebXc)
+        elif isinstance(p, Region):
+            out[k] = cheby_ball(p)
+        elif is_empty(p):
+            out[k] = (0, None)
+        else:
+            todo.append(k)
+    if todo:
+        A, b, rows = _stack([polys[k] for k in todo])
+        r, xc, status = engine.cheby_batch(A, b, rows)
+        for t, k in enumerate(todo):
+            out[k] = _store_cheby(polys[k], int(status[t]), r[t], xc[t])
+    return out
+
+
+def is_fulldim_batch(polys, abs_tol=ABS_TOL):
+    """[is_fulldim(p, abs_tol) for p in polys], batched."""
+    need = [p for p in polys if p.fulldim is None and not isinstance(p, Region)]
+    balls = dict(zip(map(id, need), cheby_ball_batch(need)))
+    out = []
+    for p in polys:
+        if p.fulldim is None:
+            if isinstance(p, Region):
+                is_fulldim(p, abs_tol)
+            else:
+                p.fulldim = balls[id(p)][0] > abs_tol
+        out.append(p.fulldim)
+    return out
+
+
+def bounding_box_batch(polys):
+    """[bounding_box(p) for p in polys] with 2*d LPs per polytope in one launch."""
+    todo = [k for k, p in enumerate(polys) if p.bbox is None]
+    if todo:
+        A, b, rows = _stack([polys[k] for k in todo])
+        lo, hi, status = engine.bbox_batch(A, b, rows)
+        for t, k in enumerate(todo):
+            bad = np.nonzero((status[t] == 1) | (status[t] == 4))[0]
+            if len(bad):
+                raise RuntimeError('bounding_box: `polytope_b200.solvers.lpsolve` returned status '
+                                   '{v} for LP {i}'.format(v=int(status[t][bad[0]]), i=int(bad[0])))
+            polys[k].bbox = lo[t].reshape(-1, 1).copy(), hi[t].reshape(-1, 1).copy()
+    return [p.bbox for p in polys]
+
+
+def reduce_batch(polys, abs_tol=ABS_TOL):
+    """[reduce(p, abs_tol=abs_tol) for p in polys] through the device pipeline."""
+    out = [None] * len(polys)
+    todo = []
+    for k, p in enumerate(polys):
+        if isinstance(p, Region):
+            out[k] = reduce(p, abs_tol=abs_tol)
+        elif p.minrep:
+            out[k] = p
+        elif p.fulldim is False or is_empty(p):
+            out[k] = Polytope()
+        else:
+            todo.append(k)
+    if todo:
+        A, b, rows = _stack([polys[k] for k in todo])
+        res = engine.reduce_batch(A, b, rows, abs_tol=abs_tol, normalize=False)
+        keeps = res.keep_lists()
+        for t, k in enumerate(todo):
+            p = polys[k]
+            if p.fulldim is None:      # is_fulldim(poly) side effects, polytope.py:1081
+                rr = res.r[t]
+                _store_cheby(p, 0 if rr == rr else 4, rr, res.xc[t])
+                p.fulldim = bool(rr > ABS_TOL)
+            if res.flags[t] & engine.F_EMPTY:
+                out[k] = Polytope()
+                continue
+            red = Polytope(res.A[t][keeps[t]], res.b[t][keeps[t]])
+            red.minrep = bool(res.flags[t] & engine.F_MINREP)
+            out[k] = red
+    return out
+
+
+# ---------------------------------------------------------------------------
+# reference-named single-object functions
+# ---------------------------------------------------------------------------
+def is_fulldim(polyreg, abs_tol=ABS_TOL):
+    """True if the polytope / region has interior points (polytope.py:962-985)."""
+    if polyreg.fulldim is not None:
+        return polyreg.fulldim
+    if len(polyreg) == 0:
+        rc, _ = cheby_ball(polyreg)
+        status = rc > abs_tol
+    else:
+        balls = cheby_ball_batch(polyreg.list_poly)
+        status = bool(np.sum([rc > abs_tol for rc, _ in balls]) > 0)
+    polyreg.fulldim = status
+    return status
+
+
+def cheby_ball(poly1):
+    """Chebyshev radius and (a) centre (polytope.py:1241-1300)."""
+    if (poly1._chebXc is not None) and (poly1._chebR is not None):
+        return poly1._chebR, poly1._chebXc
+    if isinstance(poly1, Region):
+        maxr, maxx = 0, None
+        for rc, xc in cheby_ball_batch(poly1.list_poly):
+            if rc > maxr:
+                maxr, maxx = rc, xc
+        poly1._chebXc, poly1._chebR = maxx, maxr
+        return maxr, maxx
+    if is_empty(poly1):
+        return 0, None
+    r, xc, status = engine.cheby_batch(poly1.A[None], poly1.b[None])
+    return _store_cheby(poly1, int(status[0]), r[0], xc[0])
+
+
+def bounding_box(polyreg):
+    """Smallest hyperbox (l, u) containing the polytope / region (polytope.py:1314-1411)."""
+    if polyreg.bbox is not None:
+        return polyreg.bbox
+    if isinstance(polyreg, Region):
+        boxes = bounding_box_batch(polyreg.list_poly)
+        l = np.min(np.hstack([bb[0] for bb in boxes]), axis=1).reshape(-1, 1)
+        u = np.max(np.hstack([bb[1] for bb in boxes]), axis=1).reshape(-1, 1)
+        polyreg.bbox = l, u
+        return l, u
+    return bounding_box_batch([polyreg])[0]
+
+
+def reduce(poly, nonEmptyBounded=1, abs_tol=ABS_TOL):
+    """Remove redundant inequalities (polytope.py:1053-1163), one LP per facet."""
+    if isinstance(poly, Region):
+        lst = [red for red in reduce_batch(poly.list_poly) if is_fulldim(red)]
+        if len(lst) > 0:
+            return Region(lst, poly.props)
+        return Polytope()
+    if not nonEmptyBounded:
+        raise NotImplementedError('reduce(nonEmptyBounded=0) is outside the B200 hot path')
+    return reduce_batch([poly], abs_tol=abs_tol)[0]
+
+
+def intersect(poly1, poly2, abs_tol=ABS_TOL):
+    """poly1 & poly2 for two Polytopes (polytope.py:1508-1526)."""
+    return poly1.intersect(poly2, abs_tol)
+
+
+def intersect_batch(polys1, polys2, abs_tol=ABS_TOL):
+    """[p.intersect(q) for p, q in zip(polys1, polys2)]: the pairwise, batchable
+    part of Region.intersect (polytope.py:823-826)."""
+    fd1 = is_fulldim_batch(polys1)
+    fd2 = is_fulldim_batch(polys2)
+    stacked, where = [], []
+    out = [None] * len(polys1)
+    for k, (p, q) in enumerate(zip(polys1, polys2)):
+        if not (fd1[k] and fd2[k]):
+            out[k] = Polytope()
+            continue
+        if p.dim != q.dim:
+            raise Exception("polytopes have different dimension")
+        stacked.append(Polytope(np.vstack([p.A, q.A]), np.hstack([p.b, q.b])))
+        where.append(k)
+    for k, red in zip(where, reduce_batch(stacked, abs_tol=abs_tol)):
+        out[k] = red
+    return out
+
+
+def is_adjacent(poly1, poly2, overlap=True, abs_tol=ABS_TOL):
+    """True if the two polytopes / regions touch or overlap (polytope.py:1827-1885)."""
+    if poly1.dim != poly2.dim:
+        raise Exception("is_adjacent: polytopes do not have the same dimension")
+    if isinstance(poly1, Region):
+        return any(is_adjacent(p, poly2, overlap=overlap, abs_tol=abs_tol) for p in poly1)
+    if isinstance(poly2, Region):
+        return any(is_adjacent(poly1, p, overlap=overlap, abs_tol=abs_tol) for p in poly2)
+    b1_arr = poly1.b.copy()
+    b2_arr = poly2.b.copy()
+    if overlap:
+        b1_arr += abs_tol
+        b2_arr += abs_tol
+    else:
+        M1 = np.concatenate((poly1.A, np.array([poly1.b]).T), 1).T
+        M1n = np.dot(M1, np.diag(1 / np.sqrt(np.sum(M1**2, 0))))
+        M2 = np.concatenate((poly2.A, np.array([poly2.b]).T), 1).T
+        M2n = np.dot(M2, np.diag(1 / np.sqrt(np.sum(M2**2, 0))))
+        prod = np.dot(M1n.T, M2n)
+        if not np.any(prod < -0.99):
+            return False
+        row, col = np.nonzero(np.isclose(prod, prod.min()))
+        for i, j in zip(row, col):
+            b1_arr[i] += abs_tol
+            b2_arr[j] += abs_tol
+    dummy = Polytope(np.concatenate((poly1.A, poly2.A)), np.concatenate((b1_arr, b2_arr)))
+    return is_fulldim(dummy, abs_tol=abs_tol / 10)
+
+
+def adjacency_matrix(cells, abs_tol=ABS_TOL):
+    """Dense int8 adjacency of a list of single Polytopes -- the loop of
+    find_adjacent_regions (prop2partition.py:46-63) as one kernel launch of
+    n(n-1)/2 Chebyshev LPs (cells with fewer rows are padded with zero rows,
+    which the constructor normalisation inside the kernel drops, polytope.py:130)."""
+    n = len(cells)
+    adj = np.eye(n, dtype=np.int8)
+    if n < 2:
+        return adj
+    A, b, _ = _stack(cells)
+    flags, _, _ = engine.adjacent_pairs(A, b, abs_tol=abs_tol)
+    i, j = np.tril_indices(n, -1)
+    adj[i, j] = flags
+    adj[j, i] = flags
+    return adj
