@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Headline benchmark: LPs/s on batched reduce() of random H-polytopes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one pass of the hot path over one batch: `reduce(Polytope(A, b))` for
+BASELINE.json configs[1] -- 10 000 random H-polytopes, d = 8, m = 32 (generator
+"box+cuts") -- per GPU.  An "LP" is one lpsolve-equivalent solve
+the reference algorithm needs on that input (counted by the kernels exactly as
+the oracle's call counter counts them; tests pin the equality).
+
+Printed JSON (one line, rank 0):
+  value     whole-job LPs/s with the batch resident in HBM (device-timed)
+  e2e       same metric through the public host-buffer API: pinned host (A, b)
+            -> H2D -> pipeline -> D2H of masks/flags/counts, every step
+  roofline  the dominant kernel (row LPs): algorithmic bytes / its mean device
+            time (CUDA events on the launch stream inside the library) against
+            the measured HBM peak, plus the fp64 view that actually bounds it
+  cpu_baseline  the oracle port (scipy/HiGHS, as the reference calls it) on a
+            bounded sample of the same workload, all host cores (N = 1 only)
+
+N > 1: launched by torchrun, one rank per GPU, weak scaling (each rank reduces
+its own 10 000 polytopes), one NCCL all-gather of the 64-bit keep masks per
+step; time = max over ranks.
+
+--impl reference times the reference's CPU path (the oracle port: the
+reference is pure Python over scipy; /root/reference does not travel to the GPU
+box) on a bounded sample per step, with every host core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import workloads as wl  # noqa: E402
+
+METRIC = 'LPs/sec on batched reduce() of random H-polytopes'
+CFG = dict(cfg=2, n_poly=10000, m=32, d=8)
+WORKLOAD = 'cfg2: reduce() of 10000 box+cuts H-polytopes, d=8, m=32, per GPU'
+
+
+def algorithmic_bytes(n_poly, m, d):
+    """in 8*m*(d+1) B per polytope (A|b read once), out 8 B mask + m B status."""
+    return n_poly * (8 * m * (d + 1) + 8 + m)
+
+
+def ipm_flops_per_iteration(m, n):
+    """2*(m n^2/2 + n^3/6 + 6 m n + 2 n^2) flop per interior-point iteration."""
+    return 2.0 * (m * n * n / 2.0 + n ** 3 / 6.0 + 6.0 * m * n + 2.0 * n * n)
+
+
+# --------------------------------------------------------------------------
+# CPU arm: the oracle port, all host cores
+# --------------------------------------------------------------------------
+def _cpu_chunk(args):
+    first, count = args
+    from oracle import polytope_oracle as orc
+    n = 0
+    for i in range(first, first + count):
+        A, b = wl.box_cuts(1000 * CFG['cfg'] + i, CFG['m'], CFG['d'])
+        n += orc.reduce(A, b)['n_lp']
+    return n
+
+
+def cpu_reduce_sample(n_poly, cores, first=0):
+    """Oracle reduce() on `n_poly` polytopes of the workload; -> (LPs, seconds)."""
+    import multiprocessing as mp
+    per = max(1, n_poly // (cores * 4))
+    chunks = [(first + s, min(per, n_poly - s)) for s in range(0, n_poly, per)]
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_chunk, [(0, 1)] * cores)          # warm the workers (imports)
+        t0 = time.perf_counter()
+        lps = sum(pool.map(_cpu_chunk, chunks))
+        dt = time.perf_counter() - t0
+    return lps, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    sample = 16 * cores                                  # ~25 CPU-seconds per step
+    for _ in range(args.warmup):
+        cpu_reduce_sample(cores, cores)
+    lps, secs = 0, 0.0
+    for k in range(args.steps):
+        a, b = cpu_reduce_sample(sample, cores, first=k * sample)
+        lps += a
+        secs += b
+    value = lps / secs
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'LPs/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample_polytopes_per_step': sample},
+        'cpu_baseline': {'value': value, 'unit': 'LPs/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d polytopes of cfg2 per step (%d LPs total), oracle port of the reference '
+                                   'reduce() over scipy.optimize.linprog/HiGHS, multiprocessing over all host '
+                                   'cores' % (sample, lps)},
+        'e2e': {'value': value, 'unit': 'LPs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+def run_gpu(args):
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    P, m, d = CFG['n_poly'], CFG['m'], CFG['d']
+
+    # CPU baseline first (fork-based pool must not run after CUDA is initialised)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = 16 * cores
+        lps, secs = cpu_reduce_sample(sample, cores)
+        cpu_baseline = {'value': lps / secs, 'unit': 'LPs/s', 'cores': cores, 'kind': 'port',
+                        'sample': '%d polytopes of cfg2 (%d LPs, %.1f s wall): oracle port of the reference '
+                                  'reduce() over scipy.optimize.linprog/HiGHS, multiprocessing over all host '
+                                  'cores' % (sample, lps, secs)}
+
+    import torch
+    import torch.distributed as dist
+    from polytope_b200 import engine, sharding
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
+
+    # weak scaling: rank r owns polytopes [r*P, (r+1)*P) of the seed sequence
+    A_h, b_h = wl.box_cuts_batch(CFG['cfg'], P, m, d, first=rank * P)
+    A_pin = torch.from_numpy(A_h).pin_memory()
+    b_pin = torch.from_numpy(b_h).pin_memory()
+    A_dev = A_pin.to('cuda')
+    b_dev = b_pin.to('cuda')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        res = engine.reduce_batch(A_dev, b_dev, want_A=False)
+        keep = res.keep
+        if world > 1:
+            keep = sharding.allgather_blocks(res.keep, world * P)
+        return res, keep
+
+    def step_e2e():
+        A_d = A_pin.to('cuda', non_blocking=True)
+        b_d = b_pin.to('cuda', non_blocking=True)
+        res = engine.reduce_batch(A_d, b_d, want_A=False)
+        keep = res.keep
+        if world > 1:
+            keep = sharding.allgather_blocks(res.keep, world * P)
+        return keep.cpu(), res.flags.cpu(), res.n_lp.cpu()
+
+    def timed(step, steps, profile=False):
+        """K steps, each bracketed by its own CUDA events on the launch stream,
+        L2 flushed (untimed) before every step; returns (total ms, last result, stage ms)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        stages = {}
+        out = None
+        barrier()
+        for k in range(steps):
+            flush.zero_()
+            if world > 1:
+                dist.barrier()
+            ev[k][0].record()
+            out = step()
+            ev[k][1].record()
+            if profile:
+                for name, v in engine.profile_read().items():
+                    stages[name] = stages.get(name, 0.0) + v / steps
+        barrier()
+        total = sum(a.elapsed_time(b) for a, b in ev)
+        return total, out, stages
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        step_e2e()
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = engine.launch_count()
+    t_wall0 = time.perf_counter()
+    engine.profile_enable(True)
+    ms_dev, (res, _), stages = timed(step_device, args.steps, profile=True)
+    engine.profile_enable(False)
+    launches = engine.launch_count() - launches0
+    ms_e2e, e2e_out, _ = timed(step_e2e, args.steps)
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    lps_step = int(res.n_lp.sum().item())
+    iters_step = int(res.lp_iters.sum().item())
+    t = torch.tensor([ms_dev, ms_e2e, float(lps_step)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_dev, ms_e2e, lps_all = tmax[0].item(), tmax[1].item(), tsum[2].item()
+    else:
+        lps_all = float(lps_step)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = lps_all * args.steps / (ms_dev * 1e-3)
+    e2e_value = lps_all * args.steps / (ms_e2e * 1e-3)
+    row_ms = stages.get('row_lp', float('nan'))
+    alg_bytes = algorithmic_bytes(P, m, d)
+    achieved = alg_bytes / (row_ms * 1e-3) / 1e9
+    # fp64 view: algorithmic flops of the row LPs (SURVEY 8d formula x measured iterations)
+    kept_rows = int(res.n_lp.sum().item()) - P * (1 + 2 * d)
+    row_iters = iters_step * kept_rows / max(lps_step, 1)
+    flops = row_iters * ipm_flops_per_iteration(int(round(kept_rows / P)), d)
+    h2d = A_pin.numel() * 8 + b_pin.numel() * 8
+    d2h = sum(x.numel() * x.element_size() for x in e2e_out)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'LPs/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'n_poly_per_gpu': P, 'm': m, 'd': d, 'lps_per_step_per_gpu': lps_step,
+                   'polytopes_per_s': world * P * args.steps / (ms_dev * 1e-3),
+                   'mean_ipm_iterations_per_lp': iters_step / max(lps_step, 1),
+                   'l2': 'flushed before every step (256 MiB memset, untimed); each step timed with its own '
+                         'CUDA event pair on the launch stream',
+                   'collective': 'none' if world == 1 else 'one NCCL all_gather of int64 keep masks per step'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'LPs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': launches,
+        'roofline': {'bound': 'hbm', 'kernel': 'lp_kernel<1, RowLP> (reduce row LPs)', 'achieved': achieved,
+                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
+                     'peak_source': peak_src, 'kernel_ms': row_ms, 'algorithmic_bytes': alg_bytes,
+                     'kernel_share_of_step': row_ms / (ms_dev / args.steps),
+                     'stage_ms': stages,
+                     'fp64': {'achieved_tflops': flops / (row_ms * 1e-3) / 1e12, 'peak_tflops': 35.45,
+                              'peak_source': 'DFMA microbenchmark on this pool (profiles/r01_microbench_fp64_shfl_lds.txt)',
+                              'frac': flops / (row_ms * 1e-3) / 1e12 / 35.45,
+                              'note': 'the path is fp64 latency/issue bound, not HBM bound (SURVEY.md 8d)'}},
+        'cpu_baseline': cpu_baseline,
+    }
+    traffic_file = os.path.join(ROOT, 'profiles', 'row_lp_dram_bytes.json')
+    if os.path.exists(traffic_file):
+        try:
+            line['roofline']['traffic'] = json.load(open(traffic_file)).get('dram_bytes_per_launch')
+        except (OSError, ValueError):
+            pass
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            # convenience: relaunch under torchrun on this node
+            cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+                   '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.abspath(__file__)] + sys.argv[1:]
+            return subprocess.call(cmd)
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d' % (args.gpus, world))
+    return run_gpu(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

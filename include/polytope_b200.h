@@ -98,12 +98,13 @@ int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows,
  *   b_out[P][m]     constructor-normalised b after the reference's drift
  *   A_out[P][m][d]  constructor-normalised A (nullable)
  *   n_lp[P]         LPs the reference algorithm solves for this polytope
+ *   lp_iters[P]     (nullable) interior-point iterations summed over those LPs
  *   workspace: pb200_reduce_workspace_bytes(P, m, d) bytes of device memory. */
 size_t pb200_reduce_workspace_bytes(int P, int m, int d);
 int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows,
                        int P, int m, int d, double abs_tol, int normalize,
                        uint64_t* keep, uint32_t* flags, double* r, double* xc,
-                       double* b_out, double* A_out, int32_t* n_lp,
+                       double* b_out, double* A_out, int32_t* n_lp, int32_t* lp_iters,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* is_adjacent() over T pairs of cells (single polytopes, already normalised by
@@ -119,6 +120,13 @@ int pb200_adjacent_pairs(const double* A, const double* b, int ncell, int mc, in
                          const int32_t* pair_i, const int32_t* pair_j, long long T,
                          double abs_tol, uint8_t* adjacent, double* radius,
                          int8_t* status, void* stream);
+
+/* Per-stage device times of the last pb200_reduce_batch call made while
+ * profiling was enabled: CUDA events recorded on the launch stream around the
+ * 7 stages (normalize, cheby LP, prefilter, bbox LPs, candidates, row LPs,
+ * finalize).  pb200_profile_read synchronises on the last event. */
+void pb200_profile_enable(int on);
+int pb200_profile_read(float* stage_ms, int n);
 
 /* Number of kernels this library has launched since load (bench.py's
  * `gpu_launches` evidence). */

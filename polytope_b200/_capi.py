@@ -24,7 +24,9 @@ SIGNATURES = {
     'pb200_bbox_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p] * 4),
     'pb200_reduce_workspace_bytes': (c_size_t, [c_int] * 3),
     'pb200_reduce_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_double, c_int]
-                           + [c_void_p] * 8 + [c_size_t, c_void_p]),
+                           + [c_void_p] * 9 + [c_size_t, c_void_p]),
+    'pb200_profile_enable': (None, [c_int]),
+    'pb200_profile_read': (c_int, [c_void_p, c_int]),
     'pb200_adjacent_pairs': (c_int, [c_void_p] * 2 + [c_int] * 3 + [c_void_p] * 2
                              + [c_longlong, c_double] + [c_void_p] * 4),
 }

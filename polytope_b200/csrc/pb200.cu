@@ -212,6 +212,7 @@ struct ChebyLP {
     int m, d;
     double *r, *xc;
     int8_t* status;
+    int32_t* lp_iters;           // nullable: = iterations of this LP
     __device__ int n() const { return d + 1; }
     template <int RPL>
     __device__ bool load(long long p, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
@@ -234,7 +235,10 @@ struct ChebyLP {
         const double v = res.status == ST_OPTIMAL ? res.x : nan;
         if (lane < d) xc[(size_t)p * d + lane] = v;
         if (lane == d) r[p] = v;
-        if (lane == 0) status[p] = (int8_t)res.status;
+        if (lane == 0) {
+            status[p] = (int8_t)res.status;
+            if (lp_iters) lp_iters[p] = res.iters;
+        }
     }
 };
 
@@ -247,6 +251,7 @@ struct BboxLP {
     int m, d, renorm;
     double *val_lo, *val_hi;     // [P][d] each: optimised coordinate of the lower / upper LP
     int8_t* status;              // [P][2d]
+    int32_t* lp_iters;           // nullable: += iterations
     __device__ int n() const { return d; }
     template <int RPL>
     __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
@@ -274,6 +279,7 @@ struct BboxLP {
         if (lane == i) {
             (q < d ? val_lo : val_hi)[p * d + i] = res.status == ST_OPTIMAL ? res.x : 0.0;
             status[t] = (int8_t)res.status;
+            if (lp_iters) atomicAdd(lp_iters + p, res.iters);
         }
     }
 };
@@ -289,6 +295,7 @@ struct RowLP {
     int m, d;
     double abs_tol;
     unsigned long long* keep;   // OR-accumulated
+    int32_t* lp_iters;          // nullable: += interior-point iterations of each row LP
     __device__ int n() const { return d; }
     template <int RPL>
     __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
@@ -324,6 +331,7 @@ struct RowLP {
             atomicOr(flags + p, PB200_F_LPFAIL);
         }
         if (kept) atomicOr(keep + p, 1ull << orig);
+        if (lp_iters) atomicAdd(lp_iters + p, res.iters);
     }
 };
 
@@ -408,6 +416,22 @@ __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long
 }
 
 static int g_sm_count = 0;
+
+// Optional per-stage timing of pb200_reduce_batch with CUDA events recorded on
+// the launch stream (bench.py's live roofline measurement).
+constexpr int N_STAGES = 7;   // normalize, cheby, prefilter+plan, bbox, candidates, rows, finalize
+static bool g_profile = false;
+static cudaEvent_t g_ev[N_STAGES + 1];
+static bool g_ev_ready = false, g_ev_valid = false;
+static inline void stage_mark(int i, cudaStream_t st) {
+    if (!g_profile) return;
+    if (!g_ev_ready) {
+        for (int k = 0; k <= N_STAGES; ++k) cudaEventCreate(&g_ev[k]);
+        g_ev_ready = true;
+    }
+    cudaEventRecord(g_ev[i], st);
+    if (i == N_STAGES) g_ev_valid = true;
+}
 
 template <int RPL, class Prob>
 static int launch_lp_rpl(const Prob& prob, long long n_items, int n, cudaStream_t st) {
@@ -715,7 +739,7 @@ int pb200_cheby_batch(const double* A, const double* b, const int32_t* m_rows, c
                       int d, double* r, double* xc, int8_t* status, void* stream) {
     if (P < 0 || !A || !b || !r || !xc || !status) return fail(PB200_EINVAL, "pb200_cheby_batch: null pointer");
     if (rows && m > 64) return fail(PB200_EUNSUPPORTED, "row masks need m <= 64");
-    ChebyLP prob{A, b, m_rows, rows, nullptr, 0, m, d, r, xc, status};
+    ChebyLP prob{A, b, m_rows, rows, nullptr, 0, m, d, r, xc, status, nullptr};
     return launch_lp(prob, P, m, d + 1, (cudaStream_t)stream);
 }
 
@@ -726,7 +750,7 @@ int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows, in
     if (P == 0) return PB200_OK;
     // the LP kernel writes the raw optimised coordinates into lo / hi, the
     // resolve kernel then applies the reference's status conventions in place
-    BboxLP prob{A, b, m_rows, nullptr, nullptr, 0, m, d, 0, lo, hi, status};
+    BboxLP prob{A, b, m_rows, nullptr, nullptr, 0, m, d, 0, lo, hi, status, nullptr};
     int rc = launch_lp(prob, (long long)P * 2 * d, m, d, (cudaStream_t)stream);
     if (rc) return rc;
     bbox_resolve_kernel<<<blocks_for((long long)P * d, 256), 256, 0, (cudaStream_t)stream>>>(status, P, d, lo, hi);
@@ -742,7 +766,7 @@ size_t pb200_reduce_workspace_bytes(int P, int m, int d) {
 
 int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, double abs_tol,
                        int normalize, uint64_t* keep, uint32_t* flags, double* r, double* xc, double* b_out, double* A_out,
-                       int32_t* n_lp, void* workspace, size_t workspace_bytes, void* stream) {
+                       int32_t* n_lp, int32_t* lp_iters, void* workspace, size_t workspace_bytes, void* stream) {
     if (P < 0 || !A || !b || !keep || !flags || !r || !xc || !b_out || !workspace)
         return fail(PB200_EINVAL, "pb200_reduce_batch: null pointer");
     if (m < 1 || m > 64) return fail(PB200_EUNSUPPORTED, "reduce: need 1 <= m <= 64 rows (row sets are 64-bit masks)");
@@ -753,14 +777,18 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     cudaStream_t st = (cudaStream_t)stream;
     double* An = A_out ? A_out : ws.An;
     int rc;
+    if (lp_iters) PB_CHECK_CUDA(cudaMemsetAsync(lp_iters, 0, sizeof(int32_t) * P, st));
+    stage_mark(0, st);
     // 1. constructor normalisation
     normalize_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(A, b, m_rows, P, m, d, normalize ? 1 : 0, An, ws.bn,
                                                                        ws.valid);
     ++g_launches;
     PB_CHECK_CUDA(cudaGetLastError());
+    stage_mark(1, st);
     // 2. is_fulldim: one Chebyshev LP per polytope
-    ChebyLP cheb{An, ws.bn, nullptr, ws.valid, nullptr, 0, m, d, r, xc, ws.cheb_status};
+    ChebyLP cheb{An, ws.bn, nullptr, ws.valid, nullptr, 0, m, d, r, xc, ws.cheb_status, lp_iters};
     if ((rc = launch_lp(cheb, P, m, d + 1, st))) return rc;
+    stage_mark(2, st);
     // 3. b == inf drop + duplicate-direction filter, then plan
     {
         const int wpb = 4;
@@ -773,23 +801,38 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
         ++g_launches;
         PB_CHECK_CUDA(cudaGetLastError());
     }
+    stage_mark(3, st);
     // 4. bounding box of Polytope(A_arr, b_arr) where neq > 3 nx
-    BboxLP bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus};
+    BboxLP bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
     if ((rc = launch_lp(bb, (long long)P * 2 * d, m, d, st))) return rc;
+    stage_mark(4, st);
     // 5. candidate filter
     candidate_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(An, ws.bn, ws.rows1, ws.bblo, ws.bbhi, ws.bbstatus,
                                                                        P, m, d, ws.rows2, flags);
     ++g_launches;
     PB_CHECK_CUDA(cudaGetLastError());
+    stage_mark(5, st);
     // 6. one LP per surviving row
     PB_CHECK_CUDA(cudaMemsetAsync(ws.keep_lp, 0, sizeof(uint64_t) * P, st));
-    RowLP row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, m, d, abs_tol, ws.keep_lp};
+    RowLP row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, m, d, abs_tol, ws.keep_lp, lp_iters};
     if ((rc = launch_lp(row, (long long)P * m, m, d, st))) return rc;
+    stage_mark(6, st);
     // 7. results
     finalize_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(ws.bn, ws.rows2, ws.keep_lp, flags, P, m, d, keep,
                                                                       b_out, n_lp);
     ++g_launches;
     PB_CHECK_CUDA(cudaGetLastError());
+    stage_mark(7, st);
+    return PB200_OK;
+}
+
+void pb200_profile_enable(int on) { g_profile = on != 0; g_ev_valid = false; }
+
+int pb200_profile_read(float* stage_ms, int n) {
+    if (!stage_ms || n < N_STAGES) return fail(PB200_EINVAL, "pb200_profile_read: need room for 7 stages");
+    if (!g_ev_valid) return fail(PB200_EINVAL, "pb200_profile_read: no profiled pb200_reduce_batch call yet");
+    PB_CHECK_CUDA(cudaEventSynchronize(g_ev[N_STAGES]));
+    for (int k = 0; k < N_STAGES; ++k) PB_CHECK_CUDA(cudaEventElapsedTime(stage_ms + k, g_ev[k], g_ev[k + 1]));
     return PB200_OK;
 }
 

@@ -133,8 +133,9 @@ class ReduceResult(object):
     r, xc             Chebyshev ball of each input polytope
     A, b              constructor-normalised rows; b carries the reference's drift
     n_lp   int32[P]   LPs the reference algorithm needs for this polytope
+    lp_iters int32[P] interior-point iterations summed over those LPs
     """
-    __slots__ = ('keep', 'flags', 'r', 'xc', 'A', 'b', 'n_lp')
+    __slots__ = ('keep', 'flags', 'r', 'xc', 'A', 'b', 'n_lp', 'lp_iters')
 
     def keep_lists(self):
         keep = np.asarray(self.keep.cpu() if isinstance(self.keep, torch.Tensor) else self.keep)
@@ -163,17 +164,19 @@ def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True
     b_out = torch.empty((P, m), dtype=torch.float64, device='cuda')
     A_out = torch.empty((P, m, d), dtype=torch.float64, device='cuda') if want_A else None
     n_lp = torch.empty(P, dtype=torch.int32, device='cuda')
+    lp_iters = torch.empty(P, dtype=torch.int32, device='cuda')
     ws_bytes = lib.pb200_reduce_workspace_bytes(P, m, d)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device='cuda')
     _capi.check(lib.pb200_reduce_batch(
         A.data_ptr(), b.data_ptr(), mr_ptr, P, m, d, float(abs_tol), int(bool(normalize)),
         keep.data_ptr(), flags.data_ptr(), r.data_ptr(), xc.data_ptr(), b_out.data_ptr(),
-        A_out.data_ptr() if want_A else 0, n_lp.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+        A_out.data_ptr() if want_A else 0, n_lp.data_ptr(), lp_iters.data_ptr(), ws.data_ptr(),
+        ws_bytes, _stream()),
         'pb200_reduce_batch')
-    outs = [keep, flags, r, xc, b_out, n_lp] + ([A_out] if want_A else [])
+    outs = [keep, flags, r, xc, b_out, n_lp, lp_iters] + ([A_out] if want_A else [])
     outs = _out(host, *outs)
-    res.keep, res.flags, res.r, res.xc, res.b, res.n_lp = outs[:6]
-    res.A = outs[6] if want_A else None
+    res.keep, res.flags, res.r, res.xc, res.b, res.n_lp, res.lp_iters = outs[:7]
+    res.A = outs[7] if want_A else None
     return res
 
 
@@ -199,6 +202,23 @@ def adjacent_pairs(A, b, pair_i=None, pair_j=None, abs_tol=ABS_TOL):
                                          T, float(abs_tol), adj.data_ptr(), rad.data_ptr(),
                                          status.data_ptr(), _stream()), 'pb200_adjacent_pairs')
     return _out(host, adj, rad, status)
+
+
+REDUCE_STAGES = ('normalize', 'cheby_lp', 'prefilter', 'bbox_lp', 'candidates', 'row_lp', 'finalize')
+
+
+def profile_enable(on=True):
+    """Record CUDA events around the stages of the next reduce_batch calls."""
+    _capi.lib().pb200_profile_enable(int(bool(on)))
+
+
+def profile_read():
+    """-> dict stage -> milliseconds of the last profiled reduce_batch call."""
+    import ctypes
+    buf = (ctypes.c_float * len(REDUCE_STAGES))()
+    _capi.check(_capi.lib().pb200_profile_read(ctypes.cast(buf, ctypes.c_void_p), len(REDUCE_STAGES)),
+                'pb200_profile_read')
+    return dict(zip(REDUCE_STAGES, [float(v) for v in buf]))
 
 
 def launch_count():

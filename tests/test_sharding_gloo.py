@@ -1,0 +1,57 @@
+"""world_size-2 gloo test of the multi-GPU host logic (block bounds, padded
+all-gather, result assembly) on CPU; the per-block compute is a stand-in here
+(the CUDA path needs a GPU and is covered by the -m gpu tests and bench.py)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from polytope_b200 import sharding
+
+
+def test_shard_bounds_cover_the_batch():
+    for n in (0, 1, 7, 10000, 10001):
+        for world in (1, 2, 3, 8):
+            blocks = [sharding.shard_bounds(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, n_items, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        def fn(lo, hi):          # stand-in for engine.reduce_batch on rows lo..hi
+            idx = torch.arange(lo, hi, dtype=torch.int64)
+            return idx * idx + 1, (idx % 5).to(torch.int32), torch.stack([idx, -idx], 1).double()
+        keep, flags, extra = sharding.sharded_map(fn, n_items)
+        q.put((rank, keep.numpy(), flags.numpy(), extra.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_map_world2_gloo():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    for n_items in (11, 8):
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        got = [q.get(timeout=120) for _ in range(2)]
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+        idx = np.arange(n_items)
+        for rank, keep, flags, extra in got:
+            assert np.array_equal(keep, idx * idx + 1)
+            assert np.array_equal(flags, idx % 5)
+            assert np.array_equal(extra, np.stack([idx, -idx], 1).astype(float))
