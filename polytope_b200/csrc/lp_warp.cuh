@@ -72,6 +72,7 @@ struct WarpScratch {
     double* u;   // [3][NP]   broadcast n-vectors for G u products
     double* R;   // [NSLOT][NP] results of the G'V pass
     int MP, NP, LDM;
+    int NC;      // columns allocated in G (what staging must zero)
 };
 
 __host__ __device__ inline int lp_mp(int rpl) { return 32 * rpl + 4; }
@@ -83,7 +84,7 @@ __host__ __device__ inline int lp_scratch_doubles(int rpl, int n) {
 }
 __device__ inline WarpScratch lp_carve(double* base, int rpl, int n) {
     WarpScratch w;
-    w.MP = lp_mp(rpl); w.NP = lp_np(n); w.LDM = w.NP + 1;
+    w.MP = lp_mp(rpl); w.NP = lp_np(n); w.LDM = w.NP + 1; w.NC = n;
     w.G = base;            base += n * w.MP;
     w.M = base;            base += w.NP * w.LDM;
     w.V = base;            base += NSLOT * w.MP;

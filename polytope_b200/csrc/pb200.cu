@@ -21,6 +21,7 @@
 
 #include "../../include/polytope_b200.h"
 #include "lp_warp.cuh"
+#include "lp_warp_small.cuh"
 
 namespace pb200 {
 
@@ -81,18 +82,18 @@ __device__ __forceinline__ int nth_set_bit(uint64_t mask, int k) {
 // ------------------------------------------------------------------------
 // staging helpers (one warp)
 // ------------------------------------------------------------------------
-template <int RPL>
-__device__ __forceinline__ void zero_G(const WarpScratch& w, int ncols, int lane) {
-    for (int e = lane; e < ncols * w.MP; e += 32) w.G[e] = 0.0;
+template <int RPL, class S>
+__device__ __forceinline__ void zero_G(const S& w, int lane) {
+    for (int e = lane; e < w.NC * w.MP; e += 32) w.G[e] = 0.0;
     __syncwarp();
 }
 
 // rows [0, cnt) of a row-major [.. x ld] matrix -> column-major slots; h from bp
-template <int RPL>
-__device__ __forceinline__ void stage_first_rows(const WarpScratch& w, const double* __restrict__ Ap,
-                                                 const double* __restrict__ bp, int cnt, int d, int ncols,
+template <int RPL, class S>
+__device__ __forceinline__ void stage_first_rows(const S& w, const double* __restrict__ Ap,
+                                                 const double* __restrict__ bp, int cnt, int d,
                                                  int lane, double (&h)[RPL]) {
-    zero_G<RPL>(w, ncols, lane);
+    zero_G<RPL>(w, lane);
     const int total = cnt * d;
     for (int e = lane; e < total; e += 32) {
         const int i = e / d, j = e - i * d;
@@ -107,11 +108,11 @@ __device__ __forceinline__ void stage_first_rows(const WarpScratch& w, const dou
 }
 
 // rows selected by `mask` (ascending) of a row-major [m x d] matrix -> slots 0..cnt-1
-template <int RPL>
-__device__ __forceinline__ int stage_masked_rows(const WarpScratch& w, const double* __restrict__ Ap,
-                                                 const double* __restrict__ bp, int m, int d, int ncols,
+template <int RPL, class S>
+__device__ __forceinline__ int stage_masked_rows(const S& w, const double* __restrict__ Ap,
+                                                 const double* __restrict__ bp, int m, int d,
                                                  uint64_t mask, int lane, double (&h)[RPL]) {
-    zero_G<RPL>(w, ncols, lane);
+    zero_G<RPL>(w, lane);
     const int total = m * d;
     for (int e = lane; e < total; e += 32) {
         const int i = e / d, j = e - i * d;
@@ -136,8 +137,8 @@ __device__ __forceinline__ int stage_masked_rows(const WarpScratch& w, const dou
 // Polytope.__init__ normalisation of the staged rows (polytope.py:128-138):
 // row / ||row||_2, b / ||row||_2; rows with norm <= 1e-10 are dropped (h = +inf
 // tells the solver the row does not exist).
-template <int RPL>
-__device__ __forceinline__ void renormalize_rows(const WarpScratch& w, int cnt, int d, int lane, double (&h)[RPL]) {
+template <int RPL, class S>
+__device__ __forceinline__ void renormalize_rows(const S& w, int cnt, int d, int lane, double (&h)[RPL]) {
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
         const int i = lane + 32 * r;
@@ -159,8 +160,8 @@ __device__ __forceinline__ void renormalize_rows(const WarpScratch& w, int cnt, 
 }
 
 // extra column d = ||row||_2 of the staged rows (polytope.py:1285-1286)
-template <int RPL>
-__device__ __forceinline__ void append_norm_column(const WarpScratch& w, int cnt, int d, int lane) {
+template <int RPL, class S>
+__device__ __forceinline__ void append_norm_column(const S& w, int cnt, int d, int lane) {
 #pragma unroll
     for (int r = 0; r < RPL; ++r) {
         const int i = lane + 32 * r;
@@ -184,15 +185,15 @@ struct GenericLP {
     int8_t* status;
     int32_t* iters;
     __device__ int n() const { return nn; }
-    template <int RPL>
-    __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    template <int RPL, class S>
+    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
         mm = m_rows ? min(max(m_rows[t], 0), m) : m;
-        stage_first_rows<RPL>(w, G + (size_t)t * m * nn, h + (size_t)t * m, mm, nn, nn, lane, hh);
+        stage_first_rows<RPL>(w, G + (size_t)t * m * nn, h + (size_t)t * m, mm, nn, lane, hh);
         cc = lane < nn ? c[(size_t)t * nn + lane] : 0.0;
         return true;
     }
     template <int RPL>
-    __device__ void store(long long t, const WarpScratch&, int lane, const LpResult& res) const {
+    __device__ void store(long long t, int lane, const LpResult& res) const {
         const double nan = __longlong_as_double(0x7ff8000000000000ll);
         if (lane < nn) x[(size_t)t * nn + lane] = res.status == ST_OPTIMAL ? res.x : nan;
         if (lane == 0) {
@@ -214,23 +215,23 @@ struct ChebyLP {
     int8_t* status;
     int32_t* lp_iters;           // nullable: = iterations of this LP
     __device__ int n() const { return d + 1; }
-    template <int RPL>
-    __device__ bool load(long long p, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    template <int RPL, class S>
+    __device__ bool load(long long p, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
         if (skip_flags && (skip_flags[p] & skip_mask)) return false;
         const double* Ap = A + (size_t)p * m * d;
         const double* bp = b + (size_t)p * m;
         if (rows) {
-            mm = stage_masked_rows<RPL>(w, Ap, bp, m, d, d + 1, rows[p] & low_bits(m), lane, hh);
+            mm = stage_masked_rows<RPL>(w, Ap, bp, m, d, rows[p] & low_bits(m), lane, hh);
         } else {
             mm = m_rows ? min(max(m_rows[p], 0), m) : m;
-            stage_first_rows<RPL>(w, Ap, bp, mm, d, d + 1, lane, hh);
+            stage_first_rows<RPL>(w, Ap, bp, mm, d, lane, hh);
         }
         append_norm_column<RPL>(w, mm, d, lane);
         cc = lane == d ? -1.0 : 0.0;
         return true;
     }
     template <int RPL>
-    __device__ void store(long long p, const WarpScratch&, int lane, const LpResult& res) const {
+    __device__ void store(long long p, int lane, const LpResult& res) const {
         const double nan = __longlong_as_double(0x7ff8000000000000ll);
         const double v = res.status == ST_OPTIMAL ? res.x : nan;
         if (lane < d) xc[(size_t)p * d + lane] = v;
@@ -253,18 +254,18 @@ struct BboxLP {
     int8_t* status;              // [P][2d]
     int32_t* lp_iters;           // nullable: += iterations
     __device__ int n() const { return d; }
-    template <int RPL>
-    __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    template <int RPL, class S>
+    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
         const long long p = t / (2 * d);
         const int q = (int)(t - p * 2 * d);
         if (need_flags && !(need_flags[p] & need_mask)) return false;
         const double* Ap = A + (size_t)p * m * d;
         const double* bp = b + (size_t)p * m;
         if (rows) {
-            mm = stage_masked_rows<RPL>(w, Ap, bp, m, d, d, rows[p] & low_bits(m), lane, hh);
+            mm = stage_masked_rows<RPL>(w, Ap, bp, m, d, rows[p] & low_bits(m), lane, hh);
         } else {
             mm = m_rows ? min(max(m_rows[p], 0), m) : m;
-            stage_first_rows<RPL>(w, Ap, bp, mm, d, d, lane, hh);
+            stage_first_rows<RPL>(w, Ap, bp, mm, d, lane, hh);
         }
         if (renorm) renormalize_rows<RPL>(w, mm, d, lane, hh);
         const int i = q < d ? q : q - d;
@@ -272,7 +273,7 @@ struct BboxLP {
         return true;
     }
     template <int RPL>
-    __device__ void store(long long t, const WarpScratch&, int lane, const LpResult& res) const {
+    __device__ void store(long long t, int lane, const LpResult& res) const {
         const long long p = t / (2 * d);
         const int q = (int)(t - p * 2 * d);
         const int i = q < d ? q : q - d;
@@ -297,14 +298,14 @@ struct RowLP {
     unsigned long long* keep;   // OR-accumulated
     int32_t* lp_iters;          // nullable: += interior-point iterations of each row LP
     __device__ int n() const { return d; }
-    template <int RPL>
-    __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    template <int RPL, class S>
+    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
         const long long p = t / m;
         const int k = (int)(t - p * m);
         if (!(flags[p] & run_mask)) return false;
         const uint64_t mask = rows[p] & low_bits(m);
         if (k >= __popcll(mask)) return false;
-        mm = stage_masked_rows<RPL>(w, A + (size_t)p * m * d, b + (size_t)p * m, m, d, d, mask, lane, hh);
+        mm = stage_masked_rows<RPL>(w, A + (size_t)p * m * d, b + (size_t)p * m, m, d, mask, lane, hh);
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const int i = lane + 32 * r;
@@ -315,7 +316,7 @@ struct RowLP {
         return true;
     }
     template <int RPL>
-    __device__ void store(long long t, const WarpScratch& w, int lane, const LpResult& res) const {
+    __device__ void store(long long t, int lane, const LpResult& res) const {
         const long long p = t / m;
         const int k = (int)(t - p * m);
         if (lane != 0) return;
@@ -355,12 +356,12 @@ struct AdjacentLP {
         i = (int)ii;
         j = (int)(t - ii * (ii - 1) / 2);
     }
-    template <int RPL>
-    __device__ bool load(long long t, const WarpScratch& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    template <int RPL, class S>
+    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
         int ci, cj;
         pair(t, ci, cj);
         mm = 2 * mc;
-        zero_G<RPL>(w, d + 1, lane);
+        zero_G<RPL>(w, lane);
         const int total = mc * d;
         const double* A1 = A + (size_t)ci * total;
         const double* A2 = A + (size_t)cj * total;
@@ -384,7 +385,7 @@ struct AdjacentLP {
         return true;
     }
     template <int RPL>
-    __device__ void store(long long t, const WarpScratch&, int lane, const LpResult& res) const {
+    __device__ void store(long long t, int lane, const LpResult& res) const {
         if (lane != d) return;
         const double nan = __longlong_as_double(0x7ff8000000000000ll);
         const double rr = res.status == ST_OPTIMAL ? res.x : nan;
@@ -399,7 +400,7 @@ struct AdjacentLP {
 // ------------------------------------------------------------------------
 template <int RPL, class Prob>
 __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long n_items) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n = prob.n();
     const WarpScratch w = lp_carve(smem + (size_t)wib * lp_scratch_doubles(RPL, n), RPL, n);
@@ -410,7 +411,28 @@ __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long
         double h[RPL];
         if (!prob.template load<RPL>(t, w, lane, m, c, h)) continue;
         const LpResult res = lp_solve_warp<RPL>(w, m, n, c, h);
-        prob.template store<RPL>(t, w, lane, res);
+        prob.template store<RPL>(t, lane, res);
+        __syncwarp();
+    }
+}
+
+// n <= 8: replicated-register solver (lp_warp_small.cuh)
+template <int RPL, class Prob>
+__global__ void __launch_bounds__(WPC * 32, 3) lp_kernel_small(const Prob prob, long long n_items) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = prob.n();
+    const SmallScratch w = lps_carve(smem + (size_t)wib * lps_scratch_doubles(RPL), RPL);
+    const long long stride = (long long)gridDim.x * WPC;
+    for (long long t = (long long)blockIdx.x * WPC + wib; t < n_items; t += stride) {
+        int m;
+        double cl;
+        double h[RPL];
+        if (!prob.template load<RPL>(t, w, lane, m, cl, h)) continue;
+        const SmallResult sr = lp_solve_small<RPL>(w, m, n, cl, h);
+        LpResult res;
+        res.status = sr.status; res.iters = sr.iters; res.fun = sr.fun; res.x = sr.x;
+        prob.template store<RPL>(t, lane, res);
         __syncwarp();
     }
 }
@@ -433,12 +455,9 @@ static inline void stage_mark(int i, cudaStream_t st) {
     if (i == N_STAGES) g_ev_valid = true;
 }
 
-template <int RPL, class Prob>
-static int launch_lp_rpl(const Prob& prob, long long n_items, int n, cudaStream_t st) {
-    if (n_items <= 0) return PB200_OK;
-    const size_t smem = (size_t)WPC * lp_scratch_doubles(RPL, n) * sizeof(double);
+template <class Kern, class Prob>
+static int launch_persistent(Kern kern, size_t smem, const Prob& prob, long long n_items, cudaStream_t st) {
     if (smem > 227 * 1024) return fail(PB200_EUNSUPPORTED, "LP too large for shared memory");
-    auto kern = lp_kernel<RPL, Prob>;
     PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!g_sm_count) {
         int dev = 0;
@@ -456,6 +475,16 @@ static int launch_lp_rpl(const Prob& prob, long long n_items, int n, cudaStream_
     ++g_launches;
     PB_CHECK_CUDA(cudaGetLastError());
     return PB200_OK;
+}
+
+template <int RPL, class Prob>
+static int launch_lp_rpl(const Prob& prob, long long n_items, int n, cudaStream_t st) {
+    if (n_items <= 0) return PB200_OK;
+    if (n <= NS && RPL <= 2)
+        return launch_persistent(lp_kernel_small<(RPL <= 2 ? RPL : 1), Prob>,
+                                 (size_t)WPC * lps_scratch_doubles(RPL) * sizeof(double), prob, n_items, st);
+    return launch_persistent(lp_kernel<RPL, Prob>, (size_t)WPC * lp_scratch_doubles(RPL, n) * sizeof(double), prob,
+                             n_items, st);
 }
 
 template <class Prob>
