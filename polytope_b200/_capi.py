@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpolytope_b200.so')
+# PB200_LIB lets a developer A/B-test another build of the same library
+LIB_PATH = os.environ.get('PB200_LIB') or os.path.join(_HERE, 'libpolytope_b200.so')
 
 c_void_p, c_int, c_double = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
 c_size_t, c_longlong, c_char_p = ctypes.c_size_t, ctypes.c_longlong, ctypes.c_char_p

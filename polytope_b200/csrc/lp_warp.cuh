@@ -43,17 +43,20 @@ constexpr int NSLOT = 4;                // vector slots of a G'V pass
 // scipy.optimize.linprog status codes (polytope/solvers.py:92-93)
 enum : int { ST_OPTIMAL = 0, ST_ITER_LIMIT = 1, ST_INFEASIBLE = 2, ST_UNBOUNDED = 3, ST_NUMERICAL = 4 };
 
-__device__ __forceinline__ double warp_sum(double v) {
+#ifndef PB200_REDUCE_INLINE
+#define PB200_REDUCE_INLINE __forceinline__
+#endif
+__device__ PB200_REDUCE_INLINE double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
     return v;
 }
-__device__ __forceinline__ double warp_max(double v) {
+__device__ PB200_REDUCE_INLINE double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
     return v;
 }
-__device__ __forceinline__ double warp_min(double v) {
+__device__ PB200_REDUCE_INLINE double warp_min(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, o));
     return v;
@@ -71,6 +74,7 @@ struct WarpScratch {
     double* d;   // [MP]      row weights of the M pass
     double* u;   // [3][NP]   broadcast n-vectors for G u products
     double* R;   // [NSLOT][NP] results of the G'V pass
+    double* hb;  // [MP]      staged right-hand side, kept across LPs that share G
     int MP, NP, LDM;
     int NC;      // columns allocated in G (what staging must zero)
 };
@@ -80,7 +84,7 @@ __host__ __device__ inline int lp_np(int n) { return (n + 7) & ~7; }
 // doubles of scratch one warp needs for an (RPL, n) problem
 __host__ __device__ inline int lp_scratch_doubles(int rpl, int n) {
     const int MP = lp_mp(rpl), NP = lp_np(n), LDM = NP + 1;
-    return n * MP + NP * LDM + NSLOT * MP + MP + 3 * NP + NSLOT * NP;
+    return n * MP + NP * LDM + NSLOT * MP + MP + 3 * NP + NSLOT * NP + MP;
 }
 __device__ inline WarpScratch lp_carve(double* base, int rpl, int n) {
     WarpScratch w;
@@ -90,7 +94,8 @@ __device__ inline WarpScratch lp_carve(double* base, int rpl, int n) {
     w.V = base;            base += NSLOT * w.MP;
     w.d = base;            base += w.MP;
     w.u = base;            base += 3 * w.NP;
-    w.R = base;
+    w.R = base;            base += NSLOT * w.NP;
+    w.hb = base;
     return w;
 }
 

@@ -27,10 +27,11 @@ constexpr int NVEC = 6;
 enum : int { VC = 0, VX = 1, V1 = 2, V2 = 3, V3 = 4, VS = 5 };   // c, x, x1, x2(aff), x2(cor), spare
 __host__ __device__ inline int lps_scratch_doubles(int rpl) {
     const int MP = lp_mp(rpl);
-    return NS * MP + MP + NSLOT * MP + NS * NS + NSLOT * NS + NVEC * NS;
+    return NS * MP + MP + NSLOT * MP + NS * NS + NSLOT * NS + NVEC * NS + MP;
 }
 struct SmallScratch {
     double *G, *d, *V, *M, *R, *X;
+    double* hb;  // [MP] staged right-hand side, kept across LPs that share G
     int MP;
     int NC;      // columns allocated in G (what staging must zero)
 };
@@ -43,7 +44,8 @@ __device__ inline SmallScratch lps_carve(double* base, int rpl) {
     w.V = base;  base += NSLOT * w.MP;
     w.M = base;  base += NS * NS;
     w.R = base;  base += NSLOT * NS;
-    w.X = base;
+    w.X = base;  base += NVEC * NS;
+    w.hb = base;
     return w;
 }
 
@@ -66,7 +68,7 @@ __device__ __forceinline__ double fast_rsqrt(double p) {
     return y;
 }
 
-__device__ __forceinline__ void warp_sum3(double& a, double& b, double& c) {
+__device__ PB200_REDUCE_INLINE void warp_sum3(double& a, double& b, double& c) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         const double ta = __shfl_xor_sync(FULL_MASK, a, o);
@@ -75,7 +77,26 @@ __device__ __forceinline__ void warp_sum3(double& a, double& b, double& c) {
         a += ta; b += tb; c += tc;
     }
 }
-__device__ __forceinline__ void warp_sum2(double& a, double& b) {
+// max over the warp of a non-negative step ratio, in fp32 rounded up: the step
+// is 0.99 / ratio, so an over-estimate by 1 ulp(fp32) only shortens the step.
+__device__ __forceinline__ double warp_max_ratio(double v) {
+    float f = __double2float_ru(v);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) f = fmaxf(f, __shfl_xor_sync(FULL_MASK, f, o));
+    return (double)f;
+}
+__device__ PB200_REDUCE_INLINE void warp_sum5(double& a, double& b, double& c, double& d, double& e) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ta = __shfl_xor_sync(FULL_MASK, a, o);
+        const double tb = __shfl_xor_sync(FULL_MASK, b, o);
+        const double tc = __shfl_xor_sync(FULL_MASK, c, o);
+        const double td = __shfl_xor_sync(FULL_MASK, d, o);
+        const double te = __shfl_xor_sync(FULL_MASK, e, o);
+        a += ta; b += tb; c += tc; d += td; e += te;
+    }
+}
+__device__ PB200_REDUCE_INLINE void warp_sum2(double& a, double& b) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         const double ta = __shfl_xor_sync(FULL_MASK, a, o);
@@ -117,12 +138,12 @@ __device__ __forceinline__ void s_normal_matrix(const SmallScratch& w, int mk, i
     __syncwarp();
 }
 
-// ---- replicated Cholesky: every lane factors the 8x8 matrix in Ms in
-// registers; the factor goes back to Ms as a full symmetric array
-// (M[i][j] = M[j][i] = L_ij for i > j, M[k][k] = 1/L_kk, or 0 for a skipped
-// pivot) so that forward and backward substitution both read rows.
-// `add_diag` is added to every diagonal entry first (polish regularisation).
-__device__ __noinline__ unsigned s_cholesky(double* Ms, int n, double add_diag, int lane) {
+// ---- replicated Cholesky (inlined at ONE site): every lane factors the 8x8
+// matrix in Ms in registers; the factor goes back to Ms as a full symmetric
+// array (M[i][j] = M[j][i] = L_ij for i > j, M[k][k] = 1/L_kk, or 0 for a
+// skipped pivot) so forward and backward substitution both read rows.
+// Vanishing pivots are skipped LIPSOL-style (solution component forced to 0).
+__device__ __forceinline__ unsigned s_cholesky(double* Ms, int n, double add_diag, int lane) {
     double L[NTRI];
 #pragma unroll
     for (int i = 0; i < NS; ++i)
@@ -132,20 +153,13 @@ __device__ __noinline__ unsigned s_cholesky(double* Ms, int n, double add_diag, 
             L[i * (i + 1) / 2 + j] = v.x;
             if (j + 1 <= i) L[i * (i + 1) / 2 + j + 1] = v.y;
         }
-    double dmax = 1e-300;
-#pragma unroll
-    for (int k = 0; k < NS; ++k) {
-        L[k * (k + 1) / 2 + k] += add_diag;
-        dmax = fmax(dmax, L[k * (k + 1) / 2 + k]);
-    }
-    const double floor_abs = 1e-30 * dmax;
     unsigned skipped = 0;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        const double p = L[k * (k + 1) / 2 + k];
         // original diagonal entry is still in shared memory (written back last)
-        const double thr = fmax(1e-13 * (Ms[k * NS + k] + add_diag), floor_abs);
-        const bool ok = (k < n) && (p > thr);
+        const double dgk = Ms[k * NS + k] + add_diag;
+        const double p = L[k * (k + 1) / 2 + k] + add_diag;
+        const bool ok = (k < n) && (p > 1e-13 * dgk) && (p > 1e-290);
         const double rinv = ok ? fast_rsqrt(p) : 0.0;
         skipped |= ok ? 0u : (1u << k);
         L[k * (k + 1) / 2 + k] = rinv;
@@ -181,10 +195,11 @@ __device__ __forceinline__ void load_vec(const double* src, double (&v)[NS]) {
     }
 }
 
-// ---- replicated solve of (L L') y = r, NR right-hand sides stored as
+// ---- replicated solve of (L L') y = r for the NR right-hand sides stored as
 // consecutive 8-vectors at X; solutions overwrite them.  L is read by broadcast.
+// `nrhs` (warp-uniform, <= NR) right-hand sides are actually solved.
 template <int NR>
-__device__ __noinline__ void s_solve(const double* Ms, double* X, int lane) {
+__device__ __forceinline__ void s_solve(const double* Ms, double* X, int lane, int nrhs = NR) {
     double a[NR][NS];
 #pragma unroll
     for (int v = 0; v < NR; ++v) load_vec(X + v * NS, a[v]);
@@ -193,22 +208,24 @@ __device__ __noinline__ void s_solve(const double* Ms, double* X, int lane) {
         double row[NS];
         load_vec(Ms + k * NS, row);
 #pragma unroll
-        for (int v = 0; v < NR; ++v) {
-            a[v][k] *= row[k];
+        for (int v = 0; v < NR; ++v)
+            if (v < nrhs) {
+                a[v][k] *= row[k];
 #pragma unroll
-            for (int i = k + 1; i < NS; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
-        }
+                for (int i = k + 1; i < NS; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
+            }
     }
 #pragma unroll
     for (int k = NS - 1; k >= 0; --k) {
         double row[NS];
         load_vec(Ms + k * NS, row);
 #pragma unroll
-        for (int v = 0; v < NR; ++v) {
-            a[v][k] *= row[k];
+        for (int v = 0; v < NR; ++v)
+            if (v < nrhs) {
+                a[v][k] *= row[k];
 #pragma unroll
-            for (int i = 0; i < k; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
-        }
+                for (int i = 0; i < k; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
+            }
     }
     __syncwarp();
     // lanes 0..3 (4..7) write the four 16-byte pieces of solution 0 (1)
@@ -250,6 +267,28 @@ __device__ __forceinline__ double dot8(const double (&a)[NS], const double (&b)[
     return s0 + s1;
 }
 
+// Cold path (rank-deficient G at iteration 0): does c have a component in
+// null(G)?  M already holds the skip-factor; d is the row weight vector in w.d.
+template <int RPL>
+__device__ __noinline__ bool s_objective_leaves_range(const SmallScratch& w, int mk, double cl, int lane) {
+    const bool own = lane < NS;
+    double* X3 = w.X + 4 * NS;
+    if (own) X3[lane] = cl;
+    __syncwarp();
+    s_solve<1>(w.M, X3, lane);
+    double uu[NS], gu[RPL];
+    load_vec(X3, uu);
+    s_rows_times<RPL>(w, lane, uu, gu);
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = w.d[lane + 32 * r] * gu[r];
+    __syncwarp();
+    s_gt_times_slots(w, mk, 1, lane);
+    const double back = own ? w.R[lane] : 0.0;
+    const double rmax = warp_max(fabs(cl - back)), cmax = warp_max(fabs(cl));
+    __syncwarp();
+    return rmax > 1e-9 * fmax(cmax, 1e-300);
+}
+
 struct SmallResult {
     int status, iters;
     double fun;
@@ -261,18 +300,25 @@ struct SmallResult {
 // lane+32r.  n-vectors live in the shared-memory vector file w.X[NVEC][NS]:
 // elementwise updates are done by lanes 0..7 on their own component, and every
 // lane reads whole vectors by broadcast when it needs them replicated.
+//
+// The interior-point iterations and the polish rounds are steps of ONE loop
+// (`phase`), so that the big unrolled blocks -- Cholesky, the two-rhs solve,
+// the DMMA passes -- exist once in the instruction stream: the first version
+// of this kernel was 180 KB of SASS and lost ~30 % of its cycles to
+// instruction-cache misses (profiles/r01a_*), and calling them as functions
+// cost ~900 local-memory spill instructions per LP (profiles/r01c_*).
 template <int RPL>
 __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, double cl_in, const double (&h_in)[RPL]) {
     const int lane = threadIdx.x & 31;
     const int MP = w.MP;
     const int mk = (m + 3) & ~3;
     const bool own = lane < NS;
-    double cl = own ? cl_in : 0.0;
+    const double cl0 = own ? cl_in : 0.0;
+    double cl = cl0;
     double* const Xc = w.X + VC * NS;
     double* const Xx = w.X + VX * NS;
     double* const X1 = w.X + V1 * NS;      // X1, X2 contiguous: one s_solve<2>
     double* const X2 = w.X + V2 * NS;
-    double* const X3 = w.X + V3 * NS;
     if (own) { Xc[lane] = cl; Xx[lane] = 0.0; }
 
     bool live[RPL];
@@ -300,18 +346,28 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
     bool lineal = false;
     SmallResult res;
     res.status = ST_ITER_LIMIT; res.iters = 0; res.fun = 0.0; res.x = 0.0;
+    int phase = 0, round = 0, it = 0;     // phase 0: interior point, 1: polish
+    bool act[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) act[r] = false;
+    double f0 = 0.0;
     __syncwarp();
 
 #pragma unroll 1
-    for (int it = 0; it <= LP_MAX_ITER; ++it) {
-        res.iters = it;
-        // ---- residuals ----
-        double rz[RPL], d[RPL], sinv[RPL], zinv[RPL];
-        double sz = 0.0, hz = 0.0, rz2 = 0.0, gxs2 = 0.0, cx;
+    for (int step = 0; step < LP_MAX_ITER + 8; ++step) {
+        // ---- A. rows of G times the current point (x, or x/tau while polishing) ----
+        double gx[RPL], cx;
         {
-            double x[NS], gx[RPL];
+            double x[NS], c[NS];
             load_vec(Xx, x);
             s_rows_times<RPL>(w, lane, x, gx);
+            load_vec(Xc, c);
+            cx = dot8(c, x);
+        }
+        double rz[RPL], d[RPL], sinv[RPL], zinv[RPL];
+        double sz = 0.0, hz = 0.0, rz2 = 0.0, gxs2 = 0.0;
+        if (phase == 0) {
+            res.iters = it;
 #pragma unroll
             for (int r = 0; r < RPL; ++r) {
                 const int i = lane + 32 * r;
@@ -329,219 +385,211 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                 w.V[1 * MP + i] = d[r] * h[r];
                 w.V[2 * MP + i] = z[r] - d[r] * rz[r];
             }
-            double c[NS];
-            load_vec(Xc, c);
-            cx = dot8(c, x);
-        }
-        __syncwarp();
-        s_gt_times_slots(w, mk, 3, lane);
-        s_normal_matrix(w, mk, lane);
-        warp_sum3(sz, hz, rz2);
-        const double gzl = own ? w.R[lane] : 0.0;          // (G'z)_lane
-        const double rxl = fma(cl, tau, gzl);
-        double rx2 = rxl * rxl, gz2 = gzl * gzl;
-        warp_sum2(rx2, gz2);
-        const double rt = cx + hz + kap;
-        const double mu = (sz + tau * kap) * rmu;
-        const double tinv = fast_rcp(tau);
-        // ---- termination (cvxopt conelp-style tests, squared where a norm is involved) ----
-        const double t2 = tinv * tinv;
-        const double pres2 = rz2 * t2, dres2 = rx2 * t2;       // compare with tol^2 * nh2 / nc2
-        const double pcost = cx * tinv, dcost = -hz * tinv;
-        const double gap = sz * t2;
-        double relgap = 1e300;
-        if (pcost < 0.0) relgap = gap / -pcost;
-        else if (dcost > 0.0) relgap = gap / dcost;
-        if (!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300)) { res.status = ST_NUMERICAL; break; }
-        if (pres2 <= LP_FEAS_TOL * LP_FEAS_TOL * nh2 && dres2 <= LP_FEAS_TOL * LP_FEAS_TOL * nc2 &&
-            (gap <= LP_GAP_TOL || relgap <= LP_GAP_TOL)) {
-            res.status = ST_OPTIMAL; break;
-        }
-        if (tau < 1e-3 * kap) {
-            if (hz < 0.0 && sqrt(gz2 * nh2 / nc2) <= 10.0 * LP_FEAS_TOL * (-hz)) { res.status = ST_INFEASIBLE; break; }
-            if (cx < 0.0) {
-                gxs2 = warp_sum(gxs2);
-                if (sqrt(gxs2 * nc2 / nh2) <= 10.0 * LP_FEAS_TOL * (-cx)) { res.status = ST_UNBOUNDED; break; }
+        } else {
+            if (round == 3) {
+                // polished point: accept only if no row is violated and the objective agrees
+                double slack = 1e300;
+#pragma unroll
+                for (int r = 0; r < RPL; ++r)
+                    if (live[r]) slack = fmin(slack, h[r] - gx[r]);
+                slack = warp_min(slack);
+                const double f1 = warp_sum(cl0 * xl);
+                if ((slack >= -1e-9 * fmax(1.0, hmax)) && (fabs(f1 - f0) <= 1e-6 * fmax(1.0, fabs(f0)))) {
+                    res.x = xl; res.fun = f1;
+                }
+                break;
+            }
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                rz[r] = 0.0; d[r] = 0.0; sinv[r] = 0.0; zinv[r] = 0.0;
+                w.V[lane + 32 * r] = act[r] ? h[r] - gx[r] : 0.0;
             }
         }
-        if (it == LP_MAX_ITER) break;
-        // ---- factor ----
-        const unsigned skipped = s_cholesky(w.M, n, 0.0, lane);
-        if (it == 0 && skipped) {
-            // rank-deficient G: does c have a component in null(G)?  (see lp_warp.cuh)
-            if (own) X3[lane] = cl;
-            __syncwarp();
-            s_solve<1>(w.M, X3, lane);
-            double uu[NS], gu[RPL];
-            load_vec(X3, uu);
-            s_rows_times<RPL>(w, lane, uu, gu);
+        __syncwarp();
+        s_gt_times_slots(w, mk, phase == 0 ? 3 : 1, lane);
+        const bool refactor = (phase == 0) || (round == 0);
+        if (refactor) s_normal_matrix(w, mk, lane);
+        double rxl = 0.0, rt = 0.0, mu = 0.0, tinv = 1.0;
+        if (phase == 0) {
+            const double gzl = own ? w.R[lane] : 0.0;          // (G'z)_lane
+            rxl = fma(cl, tau, gzl);
+            double rx2 = rxl * rxl;
+            warp_sum5(sz, hz, rz2, rx2, gxs2);
+            rt = cx + hz + kap;
+            mu = (sz + tau * kap) * rmu;
+            tinv = fast_rcp(tau);
+            // ---- termination (cvxopt conelp-style tests, squared where a norm is involved) ----
+            const double t2 = tinv * tinv;
+            const double pcost = cx * tinv, dcost = -hz * tinv;
+            const double gap = sz * t2;
+            // relgap <= tol  <=>  gap <= tol * (-pcost)  or  gap <= tol * dcost
+            const double gapref = pcost < 0.0 ? -pcost : (dcost > 0.0 ? dcost : 0.0);
+            if (!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300)) { res.status = ST_NUMERICAL; break; }
+            if (rz2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nh2 && rx2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nc2 &&
+                (gap <= LP_GAP_TOL || gap <= LP_GAP_TOL * gapref)) {
+                if (lineal) { res.status = ST_UNBOUNDED; break; }
+                res.status = ST_OPTIMAL;
+                // ---- extract, then polish on the active set (see lp_warp.cuh) ----
+                const double te = 1.0 / tau;
+                xl *= te;
+                f0 = warp_sum(cl0 * xl);
+                res.x = xl; res.fun = f0;
+                int nact = 0;
 #pragma unroll
-            for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = d[r] * gu[r];
-            __syncwarp();
-            s_gt_times_slots(w, mk, 1, lane);
-            const double back = own ? w.R[lane] : 0.0;
-            const double rmax = warp_max(fabs(cl - back)), cmax = warp_max(fabs(cl));
-            if (rmax > 1e-9 * fmax(cmax, 1e-300)) {
-                lineal = true;
-                cl = 0.0;
-                if (own) Xc[lane] = 0.0;
-                nc2 = 1.0;
+                for (int r = 0; r < RPL; ++r) {
+                    act[r] = live[r] && (z[r] > s[r]);
+                    nact += act[r] ? 1 : 0;
+                    w.d[lane + 32 * r] = act[r] ? 1.0 : 0.0;
+                }
+                nact = __reduce_add_sync(FULL_MASK, nact);
+                if (own) { Xx[lane] = xl; Xc[lane] = cl0; }
                 __syncwarp();
+                if (nact == 0) break;
+                phase = 1; round = 0;
                 continue;
             }
+            if (tau < 1e-3 * kap) {
+                if (hz < 0.0) {
+                    const double gz2 = warp_sum(gzl * gzl);
+                    if (sqrt(gz2 * nh2 / nc2) <= 10.0 * LP_FEAS_TOL * (-hz)) { res.status = ST_INFEASIBLE; break; }
+                }
+                if (cx < 0.0 && sqrt(gxs2 * nc2 / nh2) <= 10.0 * LP_FEAS_TOL * (-cx)) { res.status = ST_UNBOUNDED; break; }
+            }
+            if (it == LP_MAX_ITER) break;
         }
-        // ---- K [x1; z1] = [-c; h],  K [x2; z2] = [-rx; q_aff] ----
-        if (own) {
-            X1[lane] = w.R[NS + lane] - cl;
-            X2[lane] = w.R[2 * NS + lane] - rxl;
-        }
-        __syncwarp();
-        s_solve<2>(w.M, X1, lane);
-        double z1[RPL], dza[RPL], dsa[RPL];
-        double hz1 = 0.0, hz2 = 0.0, cx1, cx2;
-        {
-            double x1[NS], x2[NS], g1[RPL], g2[RPL], c[NS];
-            load_vec(X1, x1);
-            load_vec(X2, x2);
-            s_rows_times2<RPL>(w, lane, x1, x2, g1, g2);
-            load_vec(Xc, c);
-            cx1 = dot8(c, x1);
-            cx2 = dot8(c, x2);
+        // ---- factor (interior point: every step; polish: once) ----
+        if (refactor) {
+            double add_diag = 0.0;
+            if (phase == 1) {
+                double dmax = 1.0;
 #pragma unroll
-            for (int r = 0; r < RPL; ++r) {
-                z1[r] = d[r] * (g1[r] - h[r]);
-                dza[r] = d[r] * (g2[r] - (s[r] - rz[r]));
-                hz1 = fma(h[r], z1[r], hz1);
-                hz2 = fma(h[r], dza[r], hz2);
+                for (int j = 0; j < NS; ++j) dmax = fmax(dmax, w.M[j * NS + j]);
+                add_diag = 1e-9 * dmax;
+                __syncwarp();
+            }
+            const unsigned skipped = s_cholesky(w.M, n, add_diag, lane);
+            if (phase == 0 && it == 0 && skipped && !lineal) {
+                // rank-deficient G: if c has a component in null(G) the LP is unbounded
+                // whenever it is feasible -> continue with c = 0 and report 3 instead of 0
+                if (s_objective_leaves_range<RPL>(w, mk, cl, lane)) {
+                    lineal = true;
+                    cl = 0.0;
+                    if (own) Xc[lane] = 0.0;
+                    nc2 = 1.0;
+                    __syncwarp();
+                    it = 1;
+                    continue;
+                }
             }
         }
-        warp_sum2(hz1, hz2);
-        const double kot = kap * tinv;
-        const double den = cx1 + hz1 - kot;                     // < 0
-        const double rden = fast_rcp(den);
-        const double dta = (-rt + kap - cx2 - hz2) * rden;
-        const double dka = -kap - kot * dta;
-        const double kinv = fast_rcp(kap);
-        double ratio = fmax(-dta * tinv, -dka * kinv);
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            dza[r] = fma(dta, z1[r], dza[r]);
-            dsa[r] = -s[r] - s[r] * zinv[r] * dza[r];
-            if (live[r]) ratio = fmax(ratio, fmax(-dsa[r] * sinv[r], -dza[r] * zinv[r]));
-        }
-        ratio = warp_max(ratio);
-        const double alpha_aff = ratio > 1.0 ? fast_rcp(ratio) : 1.0;
-        const double om = 1.0 - alpha_aff;
-        const double sigma = om * om * om;
-        const double eta = 1.0 - sigma;
-        // ---- corrector ----
-        double bs[RPL], qc[RPL];
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            bs[r] = -s[r] * z[r] + sigma * mu - dsa[r] * dza[r];
-            qc[r] = live[r] ? -eta * rz[r] - bs[r] * zinv[r] : 0.0;
-            w.V[lane + 32 * r] = d[r] * qc[r];
-        }
-        __syncwarp();
-        s_gt_times_slots(w, mk, 1, lane);
-        if (own) X3[lane] = fma(-eta, rxl, w.R[lane]);
-        __syncwarp();
-        s_solve<1>(w.M, X3, lane);
-        double dz[RPL];
-        hz2 = 0.0;
-        {
-            double x3[NS], gc[RPL], c[NS];
-            load_vec(X3, x3);
-            s_rows_times<RPL>(w, lane, x3, gc);
-            load_vec(Xc, c);
-            cx2 = dot8(c, x3);
-#pragma unroll
-            for (int r = 0; r < RPL; ++r) {
-                dz[r] = d[r] * (gc[r] - qc[r]);
-                hz2 = fma(h[r], dz[r], hz2);
-            }
-        }
-        hz2 = warp_sum(hz2);
-        const double bk = -tau * kap + sigma * mu - dta * dka;
-        const double dtau = (-eta * rt - bk * tinv - cx2 - hz2) * rden;
-        const double dkap = (bk - kap * dtau) * tinv;
-        ratio = fmax(-dtau * tinv, -dkap * kinv);
-        double ds[RPL];
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) {
-            dz[r] = fma(dtau, z1[r], dz[r]);
-            ds[r] = (bs[r] - s[r] * dz[r]) * zinv[r];
-            if (live[r]) ratio = fmax(ratio, fmax(-ds[r] * sinv[r], -dz[r] * zinv[r]));
-        }
-        ratio = warp_max(ratio);
-        const double amax = ratio > 0.0 ? fast_rcp(ratio) : 1e30;
-        const double alpha = fmin(1.0, LP_STEP * amax);
-        if (own) {
-            xl = fma(alpha, fma(dtau, X1[lane], X3[lane]), xl);
-            Xx[lane] = xl;
-        }
-        tau = fma(alpha, dtau, tau);
-        kap = fma(alpha, dkap, kap);
-#pragma unroll
-        for (int r = 0; r < RPL; ++r)
-            if (live[r]) { s[r] = fma(alpha, ds[r], s[r]); z[r] = fma(alpha, dz[r], z[r]); }
-        __syncwarp();
-    }
-    if (lineal && res.status == ST_OPTIMAL) res.status = ST_UNBOUNDED;
-    if (res.status != ST_OPTIMAL) return res;
-
-    // ---- extract and polish (see lp_warp.cuh) ----
-    const double tinv = 1.0 / tau;
-    double xsl = xl * tinv;                       // lane-owned scaled solution
-    const double cl0 = own ? cl_in : 0.0;
-    const double f0 = warp_sum(cl0 * xsl);
-    res.x = xsl;
-    res.fun = f0;
-    bool act[RPL];
-    int nact = 0;
-#pragma unroll
-    for (int r = 0; r < RPL; ++r) {
-        act[r] = live[r] && (z[r] > s[r]);
-        nact += act[r] ? 1 : 0;
-        w.d[lane + 32 * r] = act[r] ? 1.0 : 0.0;
-    }
-    nact = __reduce_add_sync(FULL_MASK, nact);
-    if (own) Xx[lane] = xsl;
-    __syncwarp();
-    if (nact == 0) return res;
-    s_normal_matrix(w, mk, lane);
-    {
-        double dmax = 1.0;
-#pragma unroll
-        for (int j = 0; j < NS; ++j) dmax = fmax(dmax, w.M[j * NS + j]);
-        __syncwarp();
-        s_cholesky(w.M, n, 1e-9 * dmax, lane);
-    }
-    double gxp[RPL];
+        // ---- solves: interior point = predictor pair then corrector; polish = one ----
+        double z1[RPL], dza[RPL], dsa[RPL], bs[RPL], qc[RPL];
+        double x1l = 0.0, rden = 0.0, dta = 0.0, dka = 0.0, kinv = 0.0, sigma = 0.0, eta = 1.0;
+        const int npass = phase == 0 ? 2 : 1;
 #pragma unroll 1
-    for (int round = 0; round < 4; ++round) {
-        double xs[NS];
-        load_vec(Xx, xs);
-        s_rows_times<RPL>(w, lane, xs, gxp);
-        if (round == 3) break;
+        for (int pass = 0; pass < npass; ++pass) {
+            if (own) {
+                double ra, rb = 0.0;
+                if (phase == 1) ra = w.R[lane];
+                else if (pass == 0) { ra = w.R[NS + lane] - cl; rb = w.R[2 * NS + lane] - rxl; }
+                else ra = fma(-eta, rxl, w.R[lane]);
+                X1[lane] = ra;
+                X2[lane] = rb;
+            }
+            __syncwarp();
+            s_solve<2>(w.M, X1, lane, (phase == 0 && pass == 0) ? 2 : 1);
+            if (phase == 1) {
+                if (own) { xl += X1[lane]; Xx[lane] = xl; }
+                ++round;
+                __syncwarp();
+                break;
+            }
+            double g1[RPL], g2[RPL], cx1, cx2;
+            {
+                double x1[NS], x2[NS], c[NS];
+                load_vec(X1, x1);
+                load_vec(X2, x2);
+                s_rows_times2<RPL>(w, lane, x1, x2, g1, g2);
+                load_vec(Xc, c);
+                cx1 = dot8(c, x1);
+                cx2 = dot8(c, x2);
+            }
+            if (pass == 0) {
+                // K [x1; z1] = [-c; h],  K [x2; z2] = [-rx; q_aff]  -> affine direction
+                if (own) x1l = X1[lane];
+                double hz1 = 0.0, hz2 = 0.0;
 #pragma unroll
-        for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = act[r] ? h[r] - gxp[r] : 0.0;
-        __syncwarp();
-        s_gt_times_slots(w, mk, 1, lane);
-        if (own) X3[lane] = w.R[lane];
-        __syncwarp();
-        s_solve<1>(w.M, X3, lane);
-        if (own) { xsl += X3[lane]; Xx[lane] = xsl; }
-        __syncwarp();
+                for (int r = 0; r < RPL; ++r) {
+                    z1[r] = d[r] * (g1[r] - h[r]);
+                    dza[r] = d[r] * (g2[r] - (s[r] - rz[r]));
+                    hz1 = fma(h[r], z1[r], hz1);
+                    hz2 = fma(h[r], dza[r], hz2);
+                }
+                warp_sum2(hz1, hz2);
+                const double kot = kap * tinv;
+                const double den = cx1 + hz1 - kot;                     // < 0
+                rden = fast_rcp(den);
+                dta = (-rt + kap - cx2 - hz2) * rden;
+                dka = -kap - kot * dta;
+                kinv = fast_rcp(kap);
+                double ratio = fmax(-dta * tinv, -dka * kinv);
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    dza[r] = fma(dta, z1[r], dza[r]);
+                    dsa[r] = -s[r] - s[r] * zinv[r] * dza[r];
+                    if (live[r]) ratio = fmax(ratio, fmax(-dsa[r] * sinv[r], -dza[r] * zinv[r]));
+                }
+                ratio = warp_max_ratio(fmax(ratio, 0.0));
+                const double alpha_aff = ratio > 1.0 ? fast_rcp(ratio) : 1.0;
+                const double om = 1.0 - alpha_aff;
+                sigma = om * om * om;
+                eta = 1.0 - sigma;
+                // corrector right-hand side
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    bs[r] = -s[r] * z[r] + sigma * mu - dsa[r] * dza[r];
+                    qc[r] = live[r] ? -eta * rz[r] - bs[r] * zinv[r] : 0.0;
+                    w.V[lane + 32 * r] = d[r] * qc[r];
+                }
+                __syncwarp();
+                s_gt_times_slots(w, mk, 1, lane);
+            } else {
+                // combined direction and step
+                double hz2 = 0.0;
+                double dz[RPL], ds[RPL];
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    dz[r] = d[r] * (g1[r] - qc[r]);
+                    hz2 = fma(h[r], dz[r], hz2);
+                }
+                hz2 = warp_sum(hz2);
+                const double bk = -tau * kap + sigma * mu - dta * dka;
+                const double dtau = (-eta * rt - bk * tinv - cx1 - hz2) * rden;
+                const double dkap = (bk - kap * dtau) * tinv;
+                double ratio = fmax(-dtau * tinv, -dkap * kinv);
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    dz[r] = fma(dtau, z1[r], dz[r]);
+                    ds[r] = (bs[r] - s[r] * dz[r]) * zinv[r];
+                    if (live[r]) ratio = fmax(ratio, fmax(-ds[r] * sinv[r], -dz[r] * zinv[r]));
+                }
+                ratio = warp_max_ratio(fmax(ratio, 0.0));
+                const double amax = ratio > 0.0 ? fast_rcp(ratio) : 1e30;
+                const double alpha = fmin(1.0, LP_STEP * amax);
+                if (own) {
+                    xl = fma(alpha, fma(dtau, x1l, X1[lane]), xl);
+                    Xx[lane] = xl;
+                }
+                tau = fma(alpha, dtau, tau);
+                kap = fma(alpha, dkap, kap);
+#pragma unroll
+                for (int r = 0; r < RPL; ++r)
+                    if (live[r]) { s[r] = fma(alpha, ds[r], s[r]); z[r] = fma(alpha, dz[r], z[r]); }
+                ++it;
+                __syncwarp();
+            }
+        }
     }
-    double slack = 1e300;
-#pragma unroll
-    for (int r = 0; r < RPL; ++r)
-        if (live[r]) slack = fmin(slack, h[r] - gxp[r]);
-    slack = warp_min(slack);
-    const double f1 = warp_sum(cl0 * xsl);
-    const bool accept = (slack >= -1e-9 * fmax(1.0, hmax)) && (fabs(f1 - f0) <= 1e-6 * fmax(1.0, fabs(f0)));
-    if (accept) { res.x = xsl; res.fun = f1; }
     return res;
 }
 

@@ -186,7 +186,7 @@ struct GenericLP {
     int32_t* iters;
     __device__ int n() const { return nn; }
     template <int RPL, class S>
-    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL], long long& cached) const {
         mm = m_rows ? min(max(m_rows[t], 0), m) : m;
         stage_first_rows<RPL>(w, G + (size_t)t * m * nn, h + (size_t)t * m, mm, nn, lane, hh);
         cc = lane < nn ? c[(size_t)t * nn + lane] : 0.0;
@@ -216,7 +216,7 @@ struct ChebyLP {
     int32_t* lp_iters;           // nullable: = iterations of this LP
     __device__ int n() const { return d + 1; }
     template <int RPL, class S>
-    __device__ bool load(long long p, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    __device__ bool load(long long p, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL], long long& cached) const {
         if (skip_flags && (skip_flags[p] & skip_mask)) return false;
         const double* Ap = A + (size_t)p * m * d;
         const double* bp = b + (size_t)p * m;
@@ -255,19 +255,29 @@ struct BboxLP {
     int32_t* lp_iters;           // nullable: += iterations
     __device__ int n() const { return d; }
     template <int RPL, class S>
-    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL], long long& cached) const {
         const long long p = t / (2 * d);
         const int q = (int)(t - p * 2 * d);
         if (need_flags && !(need_flags[p] & need_mask)) return false;
-        const double* Ap = A + (size_t)p * m * d;
-        const double* bp = b + (size_t)p * m;
-        if (rows) {
-            mm = stage_masked_rows<RPL>(w, Ap, bp, m, d, rows[p] & low_bits(m), lane, hh);
+        if (p != cached) {          // the 2d LPs of a polytope share G and h: stage once per warp
+            const double* Ap = A + (size_t)p * m * d;
+            const double* bp = b + (size_t)p * m;
+            if (rows) {
+                mm = stage_masked_rows<RPL>(w, Ap, bp, m, d, rows[p] & low_bits(m), lane, hh);
+            } else {
+                mm = m_rows ? min(max(m_rows[p], 0), m) : m;
+                stage_first_rows<RPL>(w, Ap, bp, mm, d, lane, hh);
+            }
+            if (renorm) renormalize_rows<RPL>(w, mm, d, lane, hh);
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) w.hb[lane + 32 * r] = hh[r];
+            cached = p;
+            __syncwarp();
         } else {
-            mm = m_rows ? min(max(m_rows[p], 0), m) : m;
-            stage_first_rows<RPL>(w, Ap, bp, mm, d, lane, hh);
+            mm = rows ? __popcll(rows[p] & low_bits(m)) : (m_rows ? min(max(m_rows[p], 0), m) : m);
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) hh[r] = w.hb[lane + 32 * r];
         }
-        if (renorm) renormalize_rows<RPL>(w, mm, d, lane, hh);
         const int i = q < d ? q : q - d;
         cc = lane == i ? (q < d ? 1.0 : -1.0) : 0.0;
         return true;
@@ -299,13 +309,23 @@ struct RowLP {
     int32_t* lp_iters;          // nullable: += interior-point iterations of each row LP
     __device__ int n() const { return d; }
     template <int RPL, class S>
-    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL], long long& cached) const {
         const long long p = t / m;
         const int k = (int)(t - p * m);
         if (!(flags[p] & run_mask)) return false;
         const uint64_t mask = rows[p] & low_bits(m);
         if (k >= __popcll(mask)) return false;
-        mm = stage_masked_rows<RPL>(w, A + (size_t)p * m * d, b + (size_t)p * m, m, d, mask, lane, hh);
+        if (p != cached) {          // the row LPs of a polytope share G: stage once per warp
+            mm = stage_masked_rows<RPL>(w, A + (size_t)p * m * d, b + (size_t)p * m, m, d, mask, lane, hh);
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) w.hb[lane + 32 * r] = hh[r];
+            cached = p;
+            __syncwarp();
+        } else {
+            mm = __popcll(mask);
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) hh[r] = w.hb[lane + 32 * r];
+        }
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const int i = lane + 32 * r;
@@ -357,7 +377,7 @@ struct AdjacentLP {
         j = (int)(t - ii * (ii - 1) / 2);
     }
     template <int RPL, class S>
-    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL]) const {
+    __device__ bool load(long long t, const S& w, int lane, int& mm, double& cc, double (&hh)[RPL], long long& cached) const {
         int ci, cj;
         pair(t, ci, cj);
         mm = 2 * mc;
@@ -404,12 +424,18 @@ __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n = prob.n();
     const WarpScratch w = lp_carve(smem + (size_t)wib * lp_scratch_doubles(RPL, n), RPL, n);
-    const long long stride = (long long)gridDim.x * WPC;
-    for (long long t = (long long)blockIdx.x * WPC + wib; t < n_items; t += stride) {
+    // each warp owns a contiguous range of items, so consecutive LPs of one
+    // polytope (same G) land on the same warp and are staged once
+    const long long nwarps = (long long)gridDim.x * WPC;
+    const long long chunk = (n_items + nwarps - 1) / nwarps;
+    const long long t0 = ((long long)blockIdx.x * WPC + wib) * chunk;
+    const long long t1 = t0 + chunk < n_items ? t0 + chunk : n_items;
+    long long cached = -1;
+    for (long long t = t0; t < t1; ++t) {
         int m;
         double c;
         double h[RPL];
-        if (!prob.template load<RPL>(t, w, lane, m, c, h)) continue;
+        if (!prob.template load<RPL>(t, w, lane, m, c, h, cached)) continue;
         const LpResult res = lp_solve_warp<RPL>(w, m, n, c, h);
         prob.template store<RPL>(t, lane, res);
         __syncwarp();
@@ -417,18 +443,25 @@ __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long
 }
 
 // n <= 8: replicated-register solver (lp_warp_small.cuh)
+#ifndef PB200_SMALL_MINB
+#define PB200_SMALL_MINB 4
+#endif
 template <int RPL, class Prob>
-__global__ void __launch_bounds__(WPC * 32, 3) lp_kernel_small(const Prob prob, long long n_items) {
+__global__ void __launch_bounds__(WPC * 32, PB200_SMALL_MINB) lp_kernel_small(const Prob prob, long long n_items) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n = prob.n();
     const SmallScratch w = lps_carve(smem + (size_t)wib * lps_scratch_doubles(RPL), RPL);
-    const long long stride = (long long)gridDim.x * WPC;
-    for (long long t = (long long)blockIdx.x * WPC + wib; t < n_items; t += stride) {
+    const long long nwarps = (long long)gridDim.x * WPC;
+    const long long chunk = (n_items + nwarps - 1) / nwarps;
+    const long long t0 = ((long long)blockIdx.x * WPC + wib) * chunk;
+    const long long t1 = t0 + chunk < n_items ? t0 + chunk : n_items;
+    long long cached = -1;
+    for (long long t = t0; t < t1; ++t) {
         int m;
         double cl;
         double h[RPL];
-        if (!prob.template load<RPL>(t, w, lane, m, cl, h)) continue;
+        if (!prob.template load<RPL>(t, w, lane, m, cl, h, cached)) continue;
         const SmallResult sr = lp_solve_small<RPL>(w, m, n, cl, h);
         LpResult res;
         res.status = sr.status; res.iters = sr.iters; res.fun = sr.fun; res.x = sr.x;
