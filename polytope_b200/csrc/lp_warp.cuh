@@ -38,6 +38,7 @@ constexpr int LP_MAX_N = 32;            // columns (n-vectors are lane-owned)
 constexpr double LP_FEAS_TOL = 1e-9;
 constexpr double LP_GAP_TOL = 1e-9;
 constexpr double LP_STEP = 0.99;
+constexpr double LP_EARLY_TOL = 1e-3;      // tolerance at which the certified polish is first tried
 constexpr int NSLOT = 4;                // vector slots of a G'V pass
 
 // scipy.optimize.linprog status codes (polytope/solvers.py:92-93)

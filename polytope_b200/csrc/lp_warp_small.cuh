@@ -346,15 +346,17 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
     bool lineal = false;
     SmallResult res;
     res.status = ST_ITER_LIMIT; res.iters = 0; res.fun = 0.0; res.x = 0.0;
-    int phase = 0, round = 0, it = 0;     // phase 0: interior point, 1: polish
+    int phase = 0, round = 0, it = 0;     // phase 0: interior point, 1: polish (+ certificate)
+    bool early = false, tried = false;    // early: polish attempted at the loose tolerance
     bool act[RPL];
+    double y[RPL];                        // dual certificate on the active rows
 #pragma unroll
-    for (int r = 0; r < RPL; ++r) act[r] = false;
-    double f0 = 0.0;
+    for (int r = 0; r < RPL; ++r) { act[r] = false; y[r] = 0.0; }
+    double f0 = 0.0, xp = 0.0;            // xp: lane-owned polished point
     __syncwarp();
 
 #pragma unroll 1
-    for (int step = 0; step < LP_MAX_ITER + 8; ++step) {
+    for (int step = 0; step < LP_MAX_ITER + 16; ++step) {
         // ---- A. rows of G times the current point (x, or x/tau while polishing) ----
         double gx[RPL], cx;
         {
@@ -386,23 +388,72 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                 w.V[2 * MP + i] = z[r] - d[r] * rz[r];
             }
         } else {
-            if (round == 3) {
-                // polished point: accept only if no row is violated and the objective agrees
-                double slack = 1e300;
 #pragma unroll
-                for (int r = 0; r < RPL; ++r)
+            for (int r = 0; r < RPL; ++r) { rz[r] = 0.0; d[r] = 0.0; sinv[r] = 0.0; zinv[r] = 0.0; }
+            bool fallback = false;
+            if (round < 3) {
+                // projection rounds: residual of the active rows at the current point
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = act[r] ? h[r] - gx[r] : 0.0;
+            } else if (round == 3) {
+                // polished point: no row violated, active rows tight
+                double slack = 1e300, tight = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
                     if (live[r]) slack = fmin(slack, h[r] - gx[r]);
-                slack = warp_min(slack);
-                const double f1 = warp_sum(cl0 * xl);
-                if ((slack >= -1e-9 * fmax(1.0, hmax)) && (fabs(f1 - f0) <= 1e-6 * fmax(1.0, fabs(f0)))) {
-                    res.x = xl; res.fun = f1;
+                    if (act[r]) tight = fmax(tight, fabs(h[r] - gx[r]));
                 }
-                break;
-            }
+                slack = warp_min(slack);
+                const bool feasible = slack >= -1e-9 * fmax(1.0, hmax);
+                if (!early) {
+                    // final polish of a tightly converged iterate: objective must agree
+                    const double f1 = warp_sum(cl0 * xp);
+                    if (feasible && (fabs(f1 - f0) <= 1e-6 * fmax(1.0, fabs(f0)))) { res.x = xp; res.fun = f1; }
+                    break;
+                }
+                tight = warp_max(tight);
+                if (feasible && tight <= 1e-9 * fmax(1.0, hmax)) {
+                    // start the dual certificate: y = z / tau on the active rows
+                    const double te = 1.0 / tau;
 #pragma unroll
-            for (int r = 0; r < RPL; ++r) {
-                rz[r] = 0.0; d[r] = 0.0; sinv[r] = 0.0; zinv[r] = 0.0;
-                w.V[lane + 32 * r] = act[r] ? h[r] - gx[r] : 0.0;
+                    for (int r = 0; r < RPL; ++r) {
+                        y[r] = act[r] ? z[r] * te : 0.0;
+                        w.V[lane + 32 * r] = y[r];
+                    }
+                } else {
+                    fallback = true;
+                }
+            } else {
+                // certificate refinement: gx = G u with u = (G_B'G_B)^-1 (G_B'y + c)
+                double ymin = 1e300, ymax = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    if (act[r]) { y[r] -= gx[r]; ymin = fmin(ymin, y[r]); ymax = fmax(ymax, y[r]); }
+                    w.V[lane + 32 * r] = y[r];
+                }
+                if (round == 5) {
+                    __syncwarp();
+                    s_gt_times_slots(w, mk, 1, lane);
+                    const double rd = own ? fabs(w.R[lane] + cl0) : 0.0;      // |G_B'y + c|
+                    const double rdmax = warp_max(rd);
+                    ymin = warp_min(ymin);
+                    ymax = warp_max(ymax);
+                    if (rdmax <= 1e-9 * sqrt(nc2) && ymin >= -1e-9 * fmax(1.0, ymax)) {
+                        // primal feasible, dual feasible, complementary: optimal
+                        res.status = ST_OPTIMAL;
+                        res.x = xp;
+                        res.fun = warp_sum(cl0 * xp);
+                        break;
+                    }
+                    fallback = true;
+                }
+            }
+            if (fallback) {
+                // resume the interior-point iterations from the untouched iterate
+                phase = 0; early = false;
+                if (own) Xx[lane] = xl;
+                __syncwarp();
+                continue;
             }
         }
         __syncwarp();
@@ -425,28 +476,43 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             // relgap <= tol  <=>  gap <= tol * (-pcost)  or  gap <= tol * dcost
             const double gapref = pcost < 0.0 ? -pcost : (dcost > 0.0 ? dcost : 0.0);
             if (!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300)) { res.status = ST_NUMERICAL; break; }
-            if (rz2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nh2 && rx2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nc2 &&
-                (gap <= LP_GAP_TOL || gap <= LP_GAP_TOL * gapref)) {
-                if (lineal) { res.status = ST_UNBOUNDED; break; }
-                res.status = ST_OPTIMAL;
+            const bool converged = rz2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nh2 && rx2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nc2 &&
+                                   (gap <= LP_GAP_TOL || gap <= LP_GAP_TOL * gapref);
+            // At the loose tolerance the active set is usually already identified:
+            // try the polish there and accept it only with a full optimality
+            // certificate (primal feasible, active rows tight, y >= 0 with
+            // G_B'y + c = 0); otherwise keep iterating to the tight tolerance.
+            const bool loosely = !tried && !lineal &&
+                                 rz2 * t2 <= LP_EARLY_TOL * LP_EARLY_TOL * nh2 && rx2 * t2 <= LP_EARLY_TOL * LP_EARLY_TOL * nc2 &&
+                                 (gap <= LP_EARLY_TOL || gap <= LP_EARLY_TOL * gapref);
+            if (converged || loosely) {
+                if (converged && lineal) { res.status = ST_UNBOUNDED; break; }
+                early = !converged;
+                tried = true;
                 // ---- extract, then polish on the active set (see lp_warp.cuh) ----
                 const double te = 1.0 / tau;
-                xl *= te;
-                f0 = warp_sum(cl0 * xl);
-                res.x = xl; res.fun = f0;
+                xp = xl * te;
                 int nact = 0;
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) {
                     act[r] = live[r] && (z[r] > s[r]);
                     nact += act[r] ? 1 : 0;
-                    w.d[lane + 32 * r] = act[r] ? 1.0 : 0.0;
                 }
                 nact = __reduce_add_sync(FULL_MASK, nact);
-                if (own) { Xx[lane] = xl; Xc[lane] = cl0; }
-                __syncwarp();
-                if (nact == 0) break;
-                phase = 1; round = 0;
-                continue;
+                if (converged) {
+                    f0 = warp_sum(cl0 * xp);
+                    res.status = ST_OPTIMAL; res.x = xp; res.fun = f0;
+                    if (nact == 0) break;
+                }
+                if (nact > 0) {
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r) w.d[lane + 32 * r] = act[r] ? 1.0 : 0.0;
+                    if (own) Xx[lane] = xp;
+                    __syncwarp();
+                    phase = 1; round = 0;
+                    continue;
+                }
+                early = false;      // nothing active yet: keep iterating
             }
             if (tau < 1e-3 * kap) {
                 if (hz < 0.0) {
@@ -490,7 +556,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
         for (int pass = 0; pass < npass; ++pass) {
             if (own) {
                 double ra, rb = 0.0;
-                if (phase == 1) ra = w.R[lane];
+                if (phase == 1) ra = round < 3 ? w.R[lane] : w.R[lane] + cl0;
                 else if (pass == 0) { ra = w.R[NS + lane] - cl; rb = w.R[2 * NS + lane] - rxl; }
                 else ra = fma(-eta, rxl, w.R[lane]);
                 X1[lane] = ra;
@@ -499,7 +565,10 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             __syncwarp();
             s_solve<2>(w.M, X1, lane, (phase == 0 && pass == 0) ? 2 : 1);
             if (phase == 1) {
-                if (own) { xl += X1[lane]; Xx[lane] = xl; }
+                if (own) {
+                    if (round < 3) { xp += X1[lane]; Xx[lane] = xp; }
+                    else Xx[lane] = X1[lane];           // certificate: next step multiplies G by u
+                }
                 ++round;
                 __syncwarp();
                 break;

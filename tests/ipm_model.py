@@ -16,6 +16,7 @@ MAX_ITER = 60
 FEAS_TOL = 1e-9
 GAP_TOL = 1e-9
 STEP = 0.99
+EARLY_TOL = 1e-3      # loose tolerance at which the certified polish is first tried (small-n kernel)
 
 
 def _chol_solve_factory(M, n):
@@ -48,7 +49,7 @@ def _chol_solve_factory(M, n):
     return solve
 
 
-def solve_lp(c, G, h, max_iter=MAX_ITER, polish=True, trace=None):
+def solve_lp(c, G, h, max_iter=MAX_ITER, polish=True, trace=None, early=True):
     """Returns dict(status, x, fun, iters)."""
     c = np.asarray(c, float)
     G = np.asarray(G, float)
@@ -64,6 +65,7 @@ def solve_lp(c, G, h, max_iter=MAX_ITER, polish=True, trace=None):
     status = 1
     it = 0
     lineal = False
+    tried = False
     for it in range(max_iter + 1):
         rx = G.T @ z + c * tau
         rz = G @ x + s - h * tau
@@ -87,6 +89,14 @@ def solve_lp(c, G, h, max_iter=MAX_ITER, polish=True, trace=None):
         if pres <= FEAS_TOL and dres <= FEAS_TOL and (gap <= GAP_TOL or relgap <= GAP_TOL):
             status = 0
             break
+        if (early and not tried and not lineal and pres <= EARLY_TOL and dres <= EARLY_TOL
+                and (gap <= EARLY_TOL or relgap <= EARLY_TOL)):
+            # the active set is usually identified long before tight convergence:
+            # polish now, accept only with a full optimality certificate
+            tried = True
+            ok, xp = certified_polish(c, G, h, x / tau, s / tau, z / tau)
+            if ok:
+                return dict(status=0, x=xp, fun=float(c @ xp), iters=it)
         if hz < 0 and np.linalg.norm(G.T @ z) / (-hz) * nh / nc <= FEAS_TOL * 1e1 and tau < 1e-3 * kap:
             status = 2
             break
@@ -189,3 +199,32 @@ def polish_x(c, G, h, x, s, z, rounds=3, delta=1e-9):
     if abs(c @ xp - c @ x) > 1e-6 * max(1.0, abs(c @ x)):
         return x
     return xp
+
+
+def certified_polish(c, G, h, x, s, z, rounds=3, delta=1e-9):
+    """Polish from a loosely converged iterate, accepted only when it is provably
+    optimal: x primal feasible, the active rows tight, and y >= 0 on the active
+    rows with G_B'y + c = 0 (y found by two least-norm refinement steps from z)."""
+    act = z > s
+    if not np.any(act):
+        return False, x
+    Ga, ha = G[act], h[act]
+    n = G.shape[1]
+    Mp = Ga.T @ Ga
+    Mp[np.diag_indices(n)] += delta * max(1.0, np.max(np.diag(Mp)))
+    solve = _chol_solve_factory(Mp, n)
+    xp = x.copy()
+    for _ in range(rounds):
+        xp = xp + solve(Ga.T @ (ha - Ga @ xp))
+    scale = max(1.0, np.max(np.abs(h)))
+    if np.min(h - G @ xp) < -1e-9 * scale or np.max(np.abs(ha - Ga @ xp)) > 1e-9 * scale:
+        return False, x
+    y = z[act].copy()
+    for _ in range(2):
+        y = y - Ga @ solve(Ga.T @ y + c)
+    rd = Ga.T @ y + c
+    if np.max(np.abs(rd)) > 1e-9 * max(1.0, np.linalg.norm(c)):
+        return False, x
+    if np.min(y) < -1e-9 * max(1.0, np.max(y)):
+        return False, x
+    return True, xp
