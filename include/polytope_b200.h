@@ -121,6 +121,85 @@ int pb200_adjacent_pairs(const double* A, const double* b, int ncell, int mc, in
                          double abs_tol, uint8_t* adjacent, double* radius,
                          int8_t* status, void* stream);
 
+/* ---- point-set kernels ---------------------------- */
+
+/* contains(): which of N points (column vectors: points[d][N], exactly the
+ * d x N array the reference takes) satisfy A x - b < abs_tol for every row.
+ * Replaces: Polytope.contains, polytope/polytope.py:206-218 (any_of == 0,
+ * out[P][N]) and Region.contains, :736-748 (any_of != 0, out[N] = OR over the
+ * P member polytopes).  Products are accumulated as numpy's A.dot(points) does
+ * (OpenBLAS dgemm: fma chain over k), so the flags are bit-identical. */
+int pb200_contains_batch(const double* A, const double* b, const int32_t* m_rows,
+                         int P, int m, int d, const double* points, long long N,
+                         double abs_tol, int any_of, uint8_t* out, void* stream);
+
+/* Monte-Carlo containment count of volume().
+ * Replaces: polytope/polytope.py:1583-1591:
+ *   x = l + default_rng(seed).random((d, N)) * (u - l);  count(all(A x - b < 0)).
+ * The uniform samples are regenerated on the device from numpy's PCG64 stream:
+ * rng_state[P][4] = (state_hi, state_lo, inc_hi, inc_lo) of
+ * np.random.default_rng(seed).bit_generator.state for each polytope, so the
+ * counts equal the reference's for the same seed.  lo/hi[P][d] = bounding box.
+ * volume = prod(hi - lo) * count / N is left to the host (one multiply). */
+int pb200_volume_counts(const double* A, const double* b, const int32_t* m_rows,
+                        int P, int m, int d, const double* lo, const double* hi,
+                        long long N, const uint64_t* rng_state,
+                        unsigned long long* count, void* stream);
+
+/* quickhull's point-to-hyperplane distance sweep as a stand-alone reduction.
+ * Replaces: distance(), polytope/quickhull.py:117-121, in the assignment loops
+ * :226-246 and :316-336: dist = sum(n * p) - off (numpy summation order).
+ *   points[N][d] (row-major, as quickhull takes them), normals[F][d], offsets[F]
+ *   first_facet[N]: first facet (in order) with dist > tol, else -1   (nullable)
+ *   far_facet[N], far_dist[N]: arg-max / max of dist over all facets   (nullable) */
+int pb200_point_facet_sweep(const double* points, const double* normals,
+                            const double* offsets, long long N, int F, int d,
+                            double tol, int32_t* first_facet, int32_t* far_facet,
+                            double* far_dist, void* stream);
+
+/* ---- convex hulls and vertex enumeration ---------- */
+
+/* per-hull status written by pb200_hull_batch */
+#define PB200_HULL_OK 0
+#define PB200_HULL_FEW_POINTS 1   /* npt <= d: reference returns an empty hull (quickhull.py:155-157) */
+#define PB200_HULL_FLAT 2         /* not full-dimensional: reference returns an empty hull (:159-165) */
+#define PB200_HULL_FACET_CAP 3    /* more live facets than facet_cap: call again with a larger cap */
+#define PB200_HULL_OUT_CAP 4      /* output pool too small: *total_facets tells the size needed */
+#define PB200_HULL_SINGULAR 5     /* a facet's vertices were affinely dependent */
+
+/* Convex hulls of H point sets.
+ * Replaces: quickhull(POINTS, abs_tol), polytope/quickhull.py:141-359 (and so
+ * qhull(), polytope/polytope.py:1685-1695).
+ *   points[H][Nmax][d] row-major, n_pts[H] nullable (ragged batches), 2 <= d <= 16
+ *   facet_cap: facet slots per hull in the workspace
+ *   out_A[out_cap][d], out_b[out_cap], out_vid[out_cap][d]: facets of all hulls in
+ *     one pool: unit outer normals, offsets (A x <= b), and the input indices of the d
+ *     vertices of each (simplicial) facet, ascending
+ *   facet_off[H], facet_cnt[H]: where hull h's facets are in the pool
+ *   status[H]: PB200_HULL_*;  is_vertex[H][Nmax] (nullable): 1 for hull vertices
+ *   stats[H][2] (nullable): points inserted, facets created
+ *   total_facets (device, 1 value): facets of all hulls, also when the pool overflowed */
+size_t pb200_hull_workspace_bytes(int H, int Nmax, int d, int facet_cap);
+int pb200_hull_batch(const double* points, const int32_t* n_pts, int H, int Nmax, int d,
+                     double abs_tol, int facet_cap, double* out_A, double* out_b,
+                     int32_t* out_vid, long long out_cap, long long* facet_off,
+                     int32_t* facet_cnt, int32_t* status, uint8_t* is_vertex,
+                     int32_t* stats, long long* total_facets, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* extreme(): polar dual points Ai = A_i / (b_i - A_i . xc) of P polytopes.
+ * Replaces: polytope/polytope.py:1659-1664.  out[P][m][d] (rows >= m_rows[p] zero). */
+int pb200_dual_points(const double* A, const double* b, const int32_t* m_rows,
+                      const double* xc, int P, int m, int d, double* out, void* stream);
+
+/* extreme(): vertices from the facets (H, K) of the dual hull: V = H / K + xc
+ * after the constructor normalisation qhull()'s Polytope(A, b) applies.
+ * Replaces: polytope/polytope.py:1665-1676.  V[pool][d], same indexing as the pool. */
+int pb200_dual_facets_to_vertices(const double* hull_A, const double* hull_b,
+                                  const long long* facet_off, const int32_t* facet_cnt,
+                                  const double* xc, int P, int d, int max_cnt,
+                                  double* V, void* stream);
+
 /* Per-stage device times of the last pb200_reduce_batch call made while
  * profiling was enabled: CUDA events recorded on the launch stream around the
  * 7 stages (normalize, cheby LP, prefilter, bbox LPs, candidates, row LPs,

@@ -16,6 +16,22 @@ What it restates (all citations relative to /root/reference):
 * ``intersect``          -- Polytope.intersect, polytope/polytope.py:255-275
 * ``is_adjacent``        -- polytope/polytope.py:1827-1866 (overlap=True branch)
 * ``adjacency_matrix``   -- prop2partition.py:46-63 (find_adjacent_regions)
+* ``contains``           -- Polytope.contains, polytope/polytope.py:206-218
+* ``region_contains``    -- Region.contains, polytope/polytope.py:736-748
+* ``volume``             -- polytope/polytope.py:1529-1594 (single polytope)
+* ``grid_region``        -- polytope/polytope.py:2364-2399
+* ``pcg64_uniform``      -- numpy's PCG64 stream behind default_rng(seed).random()
+                            (the kernel regenerates it; this restatement pins the
+                            algorithm against numpy itself in tests/test_oracle.py)
+* ``qhull`` / ``extreme`` -- polytope/polytope.py:1685-1695, :1597-1682.  The
+                            reference's own quickhull.py (Barber et al. 1996) is
+                            O(|NV|^2 d^2) Python and cannot finish d >= 9
+                            (SURVEY.md section 0), so the hull itself is taken
+                            from Qhull (scipy.spatial.ConvexHull, the published
+                            implementation of the same algorithm); the hull of
+                            a point set is unique, and tests/golden/hull_cases.npz
+                            pins this oracle to the reference's outputs as sets
+                            at the sizes the reference can run (d <= 6).
 
 The arithmetic of the path lives in a third-party dependency that is NOT
 vendored under /root/reference: ``scipy.optimize.linprog`` -> HiGHS
@@ -255,3 +271,121 @@ def adjacency_matrix(cells, abs_tol=ABS_TOL):
             adj[i, j] = adj[j, i] = is_adjacent(*cells[i], *cells[j],
                                                 abs_tol=abs_tol)
     return adj
+
+
+# ---------------------------------------------------------------------------
+# contains / volume / grid_region / qhull / extreme
+# ---------------------------------------------------------------------------
+def contains(A, b, points, abs_tol=ABS_TOL):
+    """Polytope.contains, polytope.py:206-218: points are column vectors (d x N)."""
+    test = A.dot(points) - b[:, np.newaxis] < abs_tol
+    return np.all(test, axis=0)
+
+
+def region_contains(cells, points, abs_tol=ABS_TOL):
+    """Region.contains, polytope.py:736-748, over a list of (A, b)."""
+    contained = np.full(points.shape[1], False, dtype=bool)
+    for A, b in cells:
+        contained = np.logical_or(contains(A, b, points, abs_tol), contained)
+    return contained
+
+
+def volume(A, b, nsamples=None, seed=None):
+    """volume() of one normalised polytope, polytope.py:1529-1594.
+
+    Returns (vol, count, N): the estimate, the number of samples strictly
+    inside, and the number of samples drawn.
+    """
+    if not is_fulldim(A, b):
+        return 0.0, 0, 0
+    n = A.shape[1]
+    N = 50 if n == 1 else 500 if n == 2 else 3000 if n == 3 else 10000
+    if nsamples is not None:
+        N = nsamples
+    l_b, u_b = bounding_box(A, b)
+    x = (np.tile(l_b, (1, N))
+         + np.random.default_rng(seed).random((n, N))
+         * np.tile(u_b - l_b, (1, N)))
+    aux = (np.dot(A, x) - np.tile(np.array([b]).T, (1, N)))
+    aux = np.nonzero(np.all(aux < 0, 0))[0].shape[0]
+    vol = np.prod(u_b - l_b) * aux / N
+    return vol, aux, N
+
+
+def grid_points(l_b, u_b, res):
+    """The unfiltered grid of grid_region, polytope.py:2391-2396."""
+    linspaces = [np.linspace(a, bb, num=n) for a, bb, n in zip(l_b, u_b, res)]
+    points = np.meshgrid(*linspaces)
+    return np.vstack(list(map(np.ravel, points)))
+
+
+PCG_MULT = (2549297995355413924 << 64) | 4865540595714422341   # numpy/random/src/pcg64/pcg64.h
+_M128 = (1 << 128) - 1
+
+
+def pcg64_uniform(state, inc, count, skip=0):
+    """`count` doubles of Generator.random() from a PCG64 (state, inc), after
+    skipping `skip` draws: step the 128-bit LCG, output XSL-RR 128/64, take the
+    top 53 bits (numpy: pcg64_random_r + random_standard_uniform)."""
+    # jump ahead (pcg_advance_lcg_128)
+    acc_mult, acc_plus, cur_mult, cur_plus, delta = 1, 0, PCG_MULT, inc, skip
+    while delta > 0:
+        if delta & 1:
+            acc_mult = (acc_mult * cur_mult) & _M128
+            acc_plus = (acc_plus * cur_mult + cur_plus) & _M128
+        cur_plus = ((cur_mult + 1) * cur_plus) & _M128
+        cur_mult = (cur_mult * cur_mult) & _M128
+        delta >>= 1
+    state = (acc_mult * state + acc_plus) & _M128
+    out = np.empty(count)
+    for i in range(count):
+        state = (state * PCG_MULT + inc) & _M128
+        hi, lo = state >> 64, state & ((1 << 64) - 1)
+        x = hi ^ lo
+        rot = hi >> 58
+        u = ((x >> rot) | (x << ((64 - rot) & 63))) & ((1 << 64) - 1)
+        out[i] = (u >> 11) * (1.0 / 9007199254740992.0)
+    return out
+
+
+def qhull(points, abs_tol=ABS_TOL):
+    """Facets (A, b) of the convex hull of N x d points, rows normalised as the
+    Polytope constructor leaves them (polytope.py:1685-1695).  Empty arrays when
+    the reference returns Polytope() (too few points / not full-dimensional,
+    quickhull.py:155-165).  Hull from Qhull, see the module docstring."""
+    from scipy.spatial import ConvexHull, QhullError
+    points = np.asarray(points, dtype=float)
+    n, d = points.shape
+    if n <= d:
+        return np.zeros((0, d)), np.zeros(0), np.zeros((0, d))
+    s = np.linalg.svd(np.transpose(points - points[0, :]), compute_uv=False)
+    if np.sum(s > 1e-15) < d:
+        return np.zeros((0, d)), np.zeros(0), np.zeros((0, d))
+    try:
+        hull = ConvexHull(points)
+    except QhullError:
+        return np.zeros((0, d)), np.zeros(0), np.zeros((0, d))
+    eq = hull.equations                       # [normal | offset], normal . x + offset <= 0
+    A, b, _ = normalize_rows(eq[:, :-1], -eq[:, -1])
+    return A, b, points[np.sort(hull.vertices)]
+
+
+def extreme(A, b):
+    """Vertices of a bounded polytope given as raw (A, b): reduce, polar dual
+    around the Chebyshev centre, hull of the dual, map the dual facets back
+    (polytope.py:1597-1682, the nx >= 3 branch).  Returns an N x d array with
+    one row per (simplicial) facet of the dual hull, or None."""
+    red = reduce(A, b)
+    if red['empty']:
+        return None
+    Ar, br, _ = normalize_rows(red['A'], red['b'])        # Polytope(A_arr[keep], b_arr[keep]), :1161
+    rmid, xmid = cheby_ball(Ar, br)
+    if not rmid > ABS_TOL:
+        return None
+    Ai = np.zeros(Ar.shape)
+    for ii in range(Ar.shape[0]):
+        Ai[ii, :] = Ar[ii, :] / (br[ii] - np.dot(Ar[ii, :], xmid))
+    H, K, _ = qhull(Ai)
+    if len(H) == 0:
+        return None
+    return H / K[:, None] + xmid

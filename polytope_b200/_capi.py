@@ -28,6 +28,16 @@ SIGNATURES = {
                            + [c_void_p] * 9 + [c_size_t, c_void_p]),
     'pb200_profile_enable': (None, [c_int]),
     'pb200_profile_read': (c_int, [c_void_p, c_int]),
+    'pb200_contains_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_longlong, c_double, c_int,
+                                     c_void_p, c_void_p]),
+    'pb200_volume_counts': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_void_p, c_longlong]
+                            + [c_void_p] * 3),
+    'pb200_point_facet_sweep': (c_int, [c_void_p] * 3 + [c_longlong, c_int, c_int, c_double] + [c_void_p] * 4),
+    'pb200_hull_workspace_bytes': (c_size_t, [c_int] * 4),
+    'pb200_hull_batch': (c_int, [c_void_p] * 2 + [c_int] * 3 + [c_double, c_int] + [c_void_p] * 3
+                         + [c_longlong] + [c_void_p] * 7 + [c_size_t, c_void_p]),
+    'pb200_dual_points': (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 2),
+    'pb200_dual_facets_to_vertices': (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 2),
     'pb200_adjacent_pairs': (c_int, [c_void_p] * 2 + [c_int] * 3 + [c_void_p] * 2
                              + [c_longlong, c_double] + [c_void_p] * 4),
 }

@@ -1,0 +1,756 @@
+// polytope_b200: batched convex hulls (sm_100a).
+//
+// Replaces: quickhull(POINTS), polytope/quickhull.py:141-359, as called by
+// qhull() (polytope/polytope.py:1685-1695) and through it by extreme()
+// (:1654-1676, hull of the polar dual of a polytope).
+//
+// The reference grows the hull one point at a time and spends its time in
+// Python loops over facets (93 % in the O(|NV|^2 d^2) `is_neighbor` scan at
+// d = 8).  The hull itself is unique, so this kernel keeps the incremental
+// structure -- start simplex, furthest outside point, visible set, horizon,
+// cone of new facets, reassignment of the orphaned outside points
+// (quickhull.py:168-190, :248-347) -- but makes every step a data-parallel sweep
+// of one CTA over a structure-of-arrays facet store:
+//
+//   * visibility is the point-to-hyperplane distance sweep over ALL live facets
+//     (quickhull.py:117-121 with the same `> abs_tol` rule) instead of a
+//     neighbour walk, so no neighbour lists exist at all;
+//   * the horizon is found by hashing the ridges (sorted (d-1)-tuples of vertex
+//     ids) of the visible facets: a ridge seen once is on the horizon -- this
+//     replaces `is_neighbor`;
+//   * facet hyperplanes come from a (d x d) Gauss-Jordan solve of V x = 1 held in
+//     the registers of a half warp (the reference solves the equivalent
+//     (d+1) x (d+1) system, quickhull.py:66-85), two facets per warp;
+//   * one CTA owns one hull; a batch of hulls (cfg4: 1000 duals of 12-D
+//     polytopes, ~20 000 facets each) is spread over a persistent grid with a
+//     global work counter.
+//
+// Points keep their input indices, facets come out as (normal, offset, vertex
+// ids); the order of the facets is an implementation detail (the reference's
+// own order depends on an unseeded random start simplex, quickhull.py:172).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace pb200 {
+
+constexpr int HT = 256;              // threads per CTA
+constexpr int HW = HT / 32;          // warps
+constexpr int HULL_MAX_D = 16;
+constexpr unsigned FULL = 0xffffffffu;
+
+enum : int { HS_OK = 0, HS_FEW_POINTS = 1, HS_FLAT = 2, HS_FACET_CAP = 3, HS_OUT_CAP = 4, HS_SINGULAR = 5 };
+
+struct HullArgs {
+    const double* pts;        // [H][Nmax][d]
+    const int32_t* n_pts;     // nullable [H]
+    int H, Nmax, d, cap;
+    double tol;
+    char* ws;                 // per-CTA workspace slices
+    size_t ws_stride;
+    int x_in_smem;            // shifted points live in shared memory
+    double* outA;             // [out_cap][d]
+    double* outb;             // [out_cap]
+    int32_t* outV;            // [out_cap][d]
+    long long out_cap;
+    unsigned long long* out_used;
+    long long* facet_off;     // [H]
+    int32_t* facet_cnt;       // [H]
+    int32_t* status;          // [H]
+    uint8_t* is_vertex;       // nullable [H][Nmax]
+    int32_t* stats;           // nullable [H][2]: points inserted, facets created
+    int* next_hull;
+};
+
+struct HullWs {
+    double* nrm;      // [d][cap]
+    double* off;      // [cap]
+    int32_t* vid;     // [d][cap] sorted ascending per facet
+    int32_t* state;   // [cap] 1 = live
+    uint8_t* vis;     // [cap]
+    int32_t* vis_list;  // [cap]
+    int32_t* hor_list;  // [cap] ridge items f*d+i
+    int32_t* new_list;  // [cap] slots of the new facets
+    int32_t* free_stack;  // [cap]
+    uint32_t* table;  // [tab_cap]
+    double* X;        // [d][Nmax] shifted points (unless in shared memory)
+    int32_t* owner;   // [Nmax]
+    double* odist;    // [Nmax]
+    int32_t* orph;    // [Nmax] orphaned outside points of the current step
+    int32_t* cand;    // [Nmax] first new facet (index into new_list) an orphan is outside of
+};
+
+__host__ __device__ inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+__host__ __device__ inline unsigned table_cap(int cap, int d) {
+    unsigned need = 2u * (unsigned)cap * (unsigned)d;
+    unsigned t = 1024;
+    while (t < need) t <<= 1;
+    return t;
+}
+__host__ __device__ inline size_t hull_ws_bytes(int Nmax, int d, int cap, int x_in_smem) {
+    size_t s = 0;
+    s += align_up(sizeof(double) * (size_t)d * cap);
+    s += align_up(sizeof(double) * (size_t)cap);
+    s += align_up(sizeof(int32_t) * (size_t)d * cap);
+    s += align_up(sizeof(int32_t) * (size_t)cap);
+    s += align_up((size_t)cap);
+    s += 4 * align_up(sizeof(int32_t) * (size_t)cap);
+    s += align_up(sizeof(uint32_t) * (size_t)table_cap(cap, d));
+    if (!x_in_smem) s += align_up(sizeof(double) * (size_t)d * Nmax);
+    s += 3 * align_up(sizeof(int32_t) * (size_t)Nmax);
+    s += align_up(sizeof(double) * (size_t)Nmax);
+    return s;
+}
+__device__ inline HullWs hull_carve(char* p, int Nmax, int d, int cap, int x_in_smem, double* smem_x) {
+    HullWs w;
+    auto take = [&](size_t n) { char* q = p; p += align_up(n); return q; };
+    w.nrm = (double*)take(sizeof(double) * (size_t)d * cap);
+    w.off = (double*)take(sizeof(double) * (size_t)cap);
+    w.vid = (int32_t*)take(sizeof(int32_t) * (size_t)d * cap);
+    w.state = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
+    w.vis = (uint8_t*)take((size_t)cap);
+    w.vis_list = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
+    w.hor_list = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
+    w.new_list = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
+    w.free_stack = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
+    w.table = (uint32_t*)take(sizeof(uint32_t) * (size_t)table_cap(cap, d));
+    w.X = x_in_smem ? smem_x : (double*)take(sizeof(double) * (size_t)d * Nmax);
+    w.owner = (int32_t*)take(sizeof(int32_t) * (size_t)Nmax);
+    w.odist = (double*)take(sizeof(double) * (size_t)Nmax);
+    w.orph = (int32_t*)take(sizeof(int32_t) * (size_t)Nmax);
+    w.cand = (int32_t*)take(sizeof(int32_t) * (size_t)Nmax);
+    return w;
+}
+
+// ---- block-wide helpers (all HT threads must call) ----
+struct BlockScratch {
+    double dv[HW];
+    int iv[HW];
+    int cnt[2][HW];  // double-buffered warp counts of block_compact_pos
+};
+
+// arg-max with lowest-index tie break; idx < 0 means "no candidate"
+__device__ __forceinline__ void block_argmax(BlockScratch& bs, double v, int idx, double& out_v, int& out_i) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, v, o);
+        const int oi = __shfl_xor_sync(FULL, idx, o);
+        const bool take = (oi >= 0) && (idx < 0 || ov > v || (ov == v && oi < idx));
+        if (take) { v = ov; idx = oi; }
+    }
+    const int wid = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { bs.dv[wid] = v; bs.iv[wid] = idx; }
+    __syncthreads();
+    v = bs.dv[0];
+    idx = bs.iv[0];
+#pragma unroll
+    for (int w = 1; w < HW; ++w) {
+        const double ov = bs.dv[w];
+        const int oi = bs.iv[w];
+        if ((oi >= 0) && (idx < 0 || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+    }
+    out_v = v;
+    out_i = idx;
+}
+
+// ordered compaction step: threads with `flag` get consecutive positions from
+// `base` on (in thread order); every thread advances its own copy of `base`
+// identically.  One barrier per call (the warp counts are double-buffered on
+// `parity`, which every thread toggles).
+__device__ __forceinline__ int block_compact_pos(BlockScratch& bs, bool flag, int& base, int& parity) {
+    const unsigned bal = __ballot_sync(FULL, flag);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) bs.cnt[parity][wid] = __popc(bal);
+    __syncthreads();
+    int before = base, total = 0;
+#pragma unroll
+    for (int w = 0; w < HW; ++w) {
+        const int c = bs.cnt[parity][w];
+        if (w < wid) before += c;
+        total += c;
+    }
+    parity ^= 1;
+    base += total;
+    return flag ? before + __popc(bal & ((1u << lane) - 1u)) : -1;
+}
+
+// ---- ridge hashing ----
+__device__ __forceinline__ int ridge_elem(const int32_t* vid, int cap, int f, int i, int t) {
+    return vid[(size_t)(t + (t >= i ? 1 : 0)) * cap + f];
+}
+__device__ __forceinline__ uint32_t ridge_hash(const int32_t* vid, int cap, int d, int f, int i) {
+    uint32_t h = 2166136261u;
+    for (int t = 0; t < d - 1; ++t) {
+        h ^= (uint32_t)ridge_elem(vid, cap, f, i, t);
+        h *= 16777619u;
+        h ^= h >> 13;
+    }
+    h *= 0x85ebca6bu;
+    h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ bool ridge_equal(const int32_t* vid, int cap, int d, int f, int i, int g, int j) {
+    for (int t = 0; t < d - 1; ++t)
+        if (ridge_elem(vid, cap, f, i, t) != ridge_elem(vid, cap, g, j, t)) return false;
+    return true;
+}
+constexpr uint32_t DUP_BIT = 0x80000000u;
+
+// ---- facet hyperplane from its D vertices, one half warp per facet ----
+// Lane r (< D) of the group holds vertex id `myv` (sorted ascending over r).
+// Solves V x = 1 by Gauss-Jordan with row pivoting; n = x / |x|, off = 1 / |x|
+// (quickhull.py:66-85 solves the same system bordered by one row/column).
+template <int D>
+__device__ __forceinline__ bool facet_plane(const double* __restrict__ X, int ldx, int myv, int gl, double (&nk)[1], int& mycol,
+                                            double& off) {
+    double a[D + 1];
+    const bool row = gl < D;
+#pragma unroll
+    for (int k = 0; k < D; ++k) a[k] = row ? X[(size_t)k * ldx + myv] : 0.0;
+    a[D] = 1.0;
+    bool used = !row;
+    mycol = -1;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double cand = used ? -1.0 : fabs(a[k]);
+        int who = gl;
+#pragma unroll
+        for (int o = 8; o; o >>= 1) {
+            const double oc = __shfl_xor_sync(FULL, cand, o, 16);
+            const int ow = __shfl_xor_sync(FULL, who, o, 16);
+            if (oc > cand || (oc == cand && ow < who)) { cand = oc; who = ow; }
+        }
+        if (!(cand > 1e-300)) ok = false;
+        const double pv = __shfl_sync(FULL, a[k], who, 16);
+        const double rinv = 1.0 / pv;
+        const double f = (gl == who) ? 0.0 : a[k] * rinv;
+#pragma unroll
+        for (int j = k + 1; j <= D; ++j) {
+            const double pj = __shfl_sync(FULL, a[j], who, 16);
+            a[j] = fma(-f, pj, a[j]);
+        }
+        if (gl == who) { used = true; mycol = k; }
+    }
+    // lane that pivoted column k holds x_k = a[D] / a[k]
+    double xk = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+        if (mycol == k) xk = a[D] / a[k];
+    double s = xk * xk;
+#pragma unroll
+    for (int o = 8; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o, 16);
+    const double mult = sqrt(s);
+    if (!(mult > 0.0) || !(mult < 1e300)) ok = false;
+    nk[0] = xk / mult;
+    off = 1.0 / mult;
+    return ok;
+}
+
+// builds the facets listed by `get_ids` (k -> lane's vertex id) into slots new_list[k]
+template <int D, class GetId>
+__device__ __forceinline__ bool make_facets(const HullWs& w, int cap, int ldx, int count, GetId get_id) {
+    const int group = threadIdx.x >> 4, gl = threadIdx.x & 15;
+    constexpr int NG = HT / 16;
+    bool all_ok = true;
+    const int rounds = (count + NG - 1) / NG;
+    for (int rnd = 0; rnd < rounds; ++rnd) {
+        const int k = rnd * NG + group;
+        const bool act = k < count;
+        const int myv = (act && gl < D) ? get_id(k, gl) : 0;
+        double nk[1];
+        int mycol;
+        double off;
+        const bool ok = facet_plane<D>(w.X, ldx, myv, gl, nk, mycol, off);
+        if (act) {
+            const int g = w.new_list[k];
+            if (gl < D) {
+                w.vid[(size_t)gl * cap + g] = myv;
+                if (mycol >= 0) w.nrm[(size_t)mycol * cap + g] = nk[0];
+            }
+            if (gl == 0) {
+                w.off[g] = off;
+                w.state[g] = 1;
+                w.vis[g] = 0;
+            }
+            all_ok = all_ok && ok;
+        }
+    }
+    return all_ok;
+}
+
+__device__ __forceinline__ double facet_dist(const HullWs& w, int cap, int d, int f, const double* p) {
+    double acc = 0.0;
+    for (int k = 0; k < d; ++k) acc = fma(w.nrm[(size_t)k * cap + f], p[k], acc);
+    return acc - w.off[f];
+}
+
+template <int D>
+__device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch& bs, double* sh_p, double* sh_c, double* sh_q,
+                         int* sh_simplex, int* sh_flag) {
+    const int tid = threadIdx.x;
+    const int d = D, cap = a.cap, Nmax = a.Nmax;
+    const int n = a.n_pts ? min(max(a.n_pts[h], 0), Nmax) : Nmax;
+    const double* P = a.pts + (size_t)h * Nmax * d;
+    const int ldx = Nmax;
+    auto finish = [&](int status, int nfac, long long offs, int inserted, int created) {
+        if (tid == 0) {
+            a.status[h] = status;
+            a.facet_cnt[h] = nfac;
+            a.facet_off[h] = offs;
+            if (a.stats) { a.stats[2 * h] = inserted; a.stats[2 * h + 1] = created; }
+        }
+    };
+    if (a.is_vertex)
+        for (int j = tid; j < Nmax; j += HT) a.is_vertex[(size_t)h * Nmax + j] = 0;
+    if (n <= d) { finish(HS_FEW_POINTS, 0, 0, 0, 0); return; }
+
+    // ---- start simplex: lowest first coordinate, then d times the point
+    // furthest from the affine span of the points chosen so far ----
+    {
+        double bv = 0.0;
+        int bi = -1;
+        for (int j = tid; j < n; j += HT) {
+            const double v = -P[(size_t)j * d];
+            if (bi < 0 || v > bv) { bv = v; bi = j; }
+        }
+        double ov;
+        int oi;
+        block_argmax(bs, bv, bi, ov, oi);
+        if (tid == 0) sh_simplex[0] = oi;
+        __syncthreads();
+    }
+    for (int k = 1; k <= d; ++k) {
+        const int v0 = sh_simplex[0];
+        double bv = 0.0;
+        int bi = -1;
+        for (int j = tid; j < n; j += HT) {
+            double r[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) r[c] = P[(size_t)j * d + c] - P[(size_t)v0 * d + c];
+            for (int q = 0; q < k - 1; ++q) {
+                double dot = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) dot = fma(r[c], sh_q[q * D + c], dot);
+#pragma unroll
+                for (int c = 0; c < D; ++c) r[c] = fma(-dot, sh_q[q * D + c], r[c]);
+            }
+            double nn = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) nn = fma(r[c], r[c], nn);
+            if (bi < 0 || nn > bv) { bv = nn; bi = j; }
+        }
+        double ov;
+        int oi;
+        block_argmax(bs, bv, bi, ov, oi);
+        // singular values of the simplex edge matrix must exceed 1e-10 (quickhull.py:186-188)
+        if (!(ov > 1e-20)) { finish(HS_FLAT, 0, 0, 0, 0); return; }
+        if (tid == 0) {
+            sh_simplex[k] = oi;
+            double r[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) r[c] = P[(size_t)oi * d + c] - P[(size_t)v0 * d + c];
+            for (int q = 0; q < k - 1; ++q) {
+                double dot = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) dot = fma(r[c], sh_q[q * D + c], dot);
+#pragma unroll
+                for (int c = 0; c < D; ++c) r[c] = fma(-dot, sh_q[q * D + c], r[c]);
+            }
+            double nn = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) nn = fma(r[c], r[c], nn);
+            const double inv = 1.0 / sqrt(nn);
+#pragma unroll
+            for (int c = 0; c < D; ++c) sh_q[(k - 1) * D + c] = r[c] * inv;
+        }
+        __syncthreads();
+    }
+    // sort the simplex ids, centre = mean of the simplex (quickhull.py:192-196)
+    if (tid == 0) {
+        for (int i = 1; i <= d; ++i) {
+            const int v = sh_simplex[i];
+            int j = i - 1;
+            while (j >= 0 && sh_simplex[j] > v) { sh_simplex[j + 1] = sh_simplex[j]; --j; }
+            sh_simplex[j + 1] = v;
+        }
+        for (int c = 0; c < d; ++c) {
+            double s = 0.0;
+            for (int i = 0; i <= d; ++i) s += P[(size_t)sh_simplex[i] * d + c] / (double)(d + 1);
+            sh_c[c] = s;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < n * d; e += HT) {
+        const int j = e / d, c = e - j * d;
+        w.X[(size_t)c * ldx + j] = P[e] - sh_c[c];
+    }
+    for (int j = tid; j < n; j += HT) { w.owner[j] = -1; w.odist[j] = 0.0; }
+    for (int f = tid; f < cap; f += HT) { w.state[f] = 0; w.vis[f] = 0; }
+    __syncthreads();
+    if (tid <= d) w.owner[sh_simplex[tid]] = -2;
+    if (tid <= d) w.new_list[tid] = tid;
+    __syncthreads();
+    // initial facets: facet i omits simplex vertex i
+    bool ok = make_facets<D>(w, cap, ldx, d + 1, [&](int k, int gl) { return sh_simplex[gl + (gl >= k ? 1 : 0)]; });
+    int hi = d + 1, nfree = 0, inserted = d + 1, created = d + 1;
+    __syncthreads();
+    // assign every other point to the first facet it is outside of (quickhull.py:226-246)
+    for (int j = tid; j < n; j += HT) {
+        if (w.owner[j] == -2) continue;
+        double p[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = w.X[(size_t)c * ldx + j];
+        for (int f = 0; f <= d; ++f) {
+            const double dist = facet_dist(w, cap, d, f, p);
+            if (dist > a.tol) { w.owner[j] = f; w.odist[j] = dist; break; }
+        }
+    }
+    __syncthreads();
+
+    int status = HS_OK, parity = 0;
+    for (int iter = 0; iter < n; ++iter) {
+        // (a) furthest outside point
+        double bv = 0.0;
+        int bi = -1;
+        for (int j = tid; j < n; j += HT)
+            if (w.owner[j] >= 0) {
+                const double v = w.odist[j];
+                if (bi < 0 || v > bv) { bv = v; bi = j; }
+            }
+        double ov;
+        int pstar;
+        block_argmax(bs, bv, bi, ov, pstar);
+        if (pstar < 0) break;
+        if (tid < d) sh_p[tid] = w.X[(size_t)tid * ldx + pstar];
+        if (tid == 0) w.owner[pstar] = -2;
+        __syncthreads();
+        // (b) visible facets: distance sweep over the whole facet store
+        double p[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = sh_p[c];
+        int nV = 0;
+        for (int f0 = 0; f0 < hi; f0 += HT) {
+            const int f = f0 + tid;
+            bool v = false;
+            if (f < hi && w.state[f] == 1) v = facet_dist(w, cap, d, f, p) > a.tol;
+            if (f < hi) w.vis[f] = v ? 1 : 0;
+            const int pos = block_compact_pos(bs, v, nV, parity);
+            if (v) w.vis_list[pos] = f;
+        }
+        __syncthreads();
+        // (c) horizon: ridges of visible facets that occur once
+        const unsigned tcap = table_cap(cap, d);
+        unsigned tsize = 1024;
+        while (tsize < 2u * (unsigned)nV * (unsigned)d) tsize <<= 1;
+        if (tsize > tcap) tsize = tcap;
+        for (unsigned e = tid; e < tsize; e += HT) w.table[e] = 0;
+        __syncthreads();
+        const int items = nV * d;
+        for (int t = tid; t < items; t += HT) {
+            const int f = w.vis_list[t / d], i = t % d;
+            uint32_t slot = ridge_hash(w.vid, cap, d, f, i) & (tsize - 1);
+            const uint32_t me = (uint32_t)(f * d + i) + 1u;
+            for (unsigned probe = 0; probe < tsize; ++probe) {
+                uint32_t cur = atomicCAS(w.table + slot, 0u, me);
+                if (cur == 0u) break;
+                const uint32_t other = (cur & ~DUP_BIT) - 1u;
+                if (ridge_equal(w.vid, cap, d, f, i, (int)(other / d), (int)(other % d))) {
+                    atomicOr(w.table + slot, DUP_BIT);
+                    break;
+                }
+                slot = (slot + 1) & (tsize - 1);
+            }
+        }
+        __syncthreads();
+        int nH = 0;
+        for (int t0 = 0; t0 < items; t0 += HT) {
+            const int t = t0 + tid;
+            bool horizon = false;
+            int item = 0;
+            if (t < items) {
+                const int f = w.vis_list[t / d], i = t % d;
+                item = f * d + i;
+                uint32_t slot = ridge_hash(w.vid, cap, d, f, i) & (tsize - 1);
+                for (unsigned probe = 0; probe < tsize; ++probe) {
+                    const uint32_t cur = w.table[slot];
+                    if (cur == 0u) break;
+                    const uint32_t other = (cur & ~DUP_BIT) - 1u;
+                    if (other == (uint32_t)item || ridge_equal(w.vid, cap, d, f, i, (int)(other / d), (int)(other % d))) {
+                        horizon = !(cur & DUP_BIT);
+                        break;
+                    }
+                    slot = (slot + 1) & (tsize - 1);
+                }
+            }
+            const int pos = block_compact_pos(bs, horizon, nH, parity);
+            if (horizon && pos < cap) w.hor_list[pos] = item;
+        }
+        __syncthreads();
+        // (d) slots for the cone of new facets: recycled ones first, then fresh ones
+        const int from_free = min(nH, nfree);
+        const int fresh = nH - from_free;
+        if (hi + fresh > cap || nH > cap) { status = HS_FACET_CAP; break; }
+        for (int k = tid; k < nH; k += HT) w.new_list[k] = k < from_free ? w.free_stack[nfree - 1 - k] : hi + (k - from_free);
+        __syncthreads();
+        // (e) new facets = horizon ridge + the new point
+        ok = make_facets<D>(w, cap, ldx, nH, [&](int k, int gl) {
+            const int item = w.hor_list[k];
+            const int f = item / d, i = item - f * d;
+            // position of pstar in the sorted ridge
+            int pos = 0;
+            for (int t = 0; t < d - 1; ++t) pos += ridge_elem(w.vid, cap, f, i, t) < pstar ? 1 : 0;
+            if (gl == pos) return pstar;
+            return ridge_elem(w.vid, cap, f, i, gl < pos ? gl : gl - 1);
+        }) && ok;
+        __syncthreads();
+        // (f) orphaned outside points go to the first new facet (in cone order) they are
+        // outside of (quickhull.py:316-336): all (facet, orphan) pairs in parallel
+        int nO = 0;
+        for (int j0 = 0; j0 < n; j0 += HT) {
+            const int j = j0 + tid;
+            bool orphan = false;
+            if (j < n) {
+                const int o = w.owner[j];
+                orphan = o >= 0 && w.vis[o];
+            }
+            const int pos = block_compact_pos(bs, orphan, nO, parity);
+            if (orphan) { w.orph[pos] = j; w.cand[j] = 0x7fffffff; }
+        }
+        __syncthreads();
+        if (nO > 0) {
+            const long long pairs = (long long)nH * nO;
+            for (long long t = tid; t < pairs; t += HT) {
+                const int k = (int)(t / nO);
+                const int j = w.orph[(int)(t - (long long)k * nO)];
+                if (w.cand[j] < k) continue;
+                double q[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) q[c] = w.X[(size_t)c * ldx + j];
+                if (facet_dist(w, cap, d, w.new_list[k], q) > a.tol) atomicMin(w.cand + j, k);
+            }
+            __syncthreads();
+            for (int o = tid; o < nO; o += HT) {
+                const int j = w.orph[o];
+                const int k = w.cand[j];
+                if (k == 0x7fffffff) { w.owner[j] = -1; w.odist[j] = 0.0; continue; }
+                double q[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) q[c] = w.X[(size_t)c * ldx + j];
+                const int g = w.new_list[k];
+                w.owner[j] = g;
+                w.odist[j] = facet_dist(w, cap, d, g, q);
+            }
+        }
+        __syncthreads();
+        // (g) retire the visible facets
+        for (int k = tid; k < nV; k += HT) {
+            const int f = w.vis_list[k];
+            w.state[f] = 0;
+            w.vis[f] = 0;
+            w.free_stack[nfree - from_free + k] = f;
+        }
+        nfree = nfree - from_free + nV;
+        hi += fresh;
+        ++inserted;
+        created += nH;
+        __syncthreads();
+    }
+    if (status == HS_OK && !ok) status = HS_SINGULAR;
+    if (status != HS_OK) { finish(status, 0, 0, inserted, created); return; }
+
+    // ---- output: live facets, b = off + n . centre (quickhull.py:348-359) ----
+    int nF = 0;
+    for (int f0 = 0; f0 < hi; f0 += HT) {
+        const int f = f0 + tid;
+        const bool live = f < hi && w.state[f] == 1;
+        const int pos = block_compact_pos(bs, live, nF, parity);
+        if (live) w.vis_list[pos] = f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long o = atomicAdd(a.out_used, (unsigned long long)nF);
+        *reinterpret_cast<volatile long long*>(sh_flag) = (long long)o;
+    }
+    __syncthreads();
+    const long long o = *reinterpret_cast<volatile long long*>(sh_flag);
+    if (o + nF > a.out_cap) { finish(HS_OUT_CAP, nF, o, inserted, created); return; }
+    for (int k = tid; k < nF; k += HT) {
+        const int f = w.vis_list[k];
+        double dot = 0.0;
+        for (int c = 0; c < d; ++c) {
+            const double nc = w.nrm[(size_t)c * cap + f];
+            a.outA[(size_t)(o + k) * d + c] = nc;
+            dot = fma(nc, sh_c[c], dot);
+            const int v = w.vid[(size_t)c * cap + f];
+            a.outV[(size_t)(o + k) * d + c] = v;
+            if (a.is_vertex) a.is_vertex[(size_t)h * Nmax + v] = 1;
+        }
+        a.outb[o + k] = w.off[f] + dot;
+    }
+    finish(HS_OK, nF, o, inserted, created);
+}
+
+template <int D>
+__global__ void __launch_bounds__(HT) hull_kernel(const HullArgs a) {
+    extern __shared__ __align__(16) double smem_x[];
+    __shared__ BlockScratch bs;
+    __shared__ double sh_p[HULL_MAX_D], sh_c[HULL_MAX_D], sh_q[HULL_MAX_D * HULL_MAX_D];
+    __shared__ int sh_simplex[HULL_MAX_D + 1];
+    __shared__ __align__(8) int sh_flag[2];
+    __shared__ int sh_h;
+    const HullWs w = hull_carve(a.ws + (size_t)blockIdx.x * a.ws_stride, a.Nmax, a.d, a.cap, a.x_in_smem, smem_x);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh_h = atomicAdd(a.next_hull, 1);
+        __syncthreads();
+        const int h = sh_h;
+        if (h >= a.H) break;
+        hull_one<D>(a, w, h, bs, sh_p, sh_c, sh_q, sh_simplex, sh_flag);
+    }
+}
+
+template <int D>
+static int launch_hull(const HullArgs& a, int grid, size_t smem, cudaStream_t st) {
+    PB_CHECK_CUDA(cudaFuncSetAttribute(hull_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hull_kernel<D><<<grid, HT, smem, st>>>(a);
+    count_launch();
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
+static int hull_grid(int H) {
+    const int sms = sm_count();
+    if (!sms) return 0;
+    const int g = 2 * sms;
+    return H < g ? H : g;
+}
+static int hull_x_in_smem(int Nmax, int d) { return (size_t)Nmax * d * sizeof(double) <= 96 * 1024 ? 1 : 0; }
+
+// polar dual points of extreme(): Ai = A_i / (b_i - A_i . xc), polytope.py:1659-1664
+__global__ void dual_points_kernel(const double* __restrict__ A, const double* __restrict__ b, const int32_t* __restrict__ m_rows,
+                                   const double* __restrict__ xc, int P, int m, int d, double* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)P * m) return;
+    const long long p = t / m;
+    const int i = (int)(t - p * m);
+    const int mm = m_rows ? min(max(m_rows[p], 0), m) : m;
+    const double* row = A + (size_t)t * d;
+    double* o = out + (size_t)t * d;
+    if (i >= mm) {
+        for (int k = 0; k < d; ++k) o[k] = 0.0;
+        return;
+    }
+    // np.dot(A[ii, :], xmid): a length-d ddot; numpy uses pairwise-free BLAS ddot, decisions do not depend on its last bit
+    double dot = 0.0;
+    for (int k = 0; k < d; ++k) dot = fma(row[k], xc[(size_t)p * d + k], dot);
+    const double den = __dsub_rn(b[t], dot);
+    for (int k = 0; k < d; ++k) o[k] = __ddiv_rn(row[k], den);
+}
+
+// vertices of the primal from the facets of the dual hull: V = H / K + xmid, polytope.py:1671-1676
+__global__ void dual_facets_to_vertices_kernel(const double* __restrict__ HA, const double* __restrict__ Hb,
+                                               const long long* __restrict__ facet_off, const int32_t* __restrict__ facet_cnt,
+                                               const double* __restrict__ xc, int P, int d, double* __restrict__ V) {
+    const int p = blockIdx.y;
+    const long long o = facet_off[p];
+    const int cnt = facet_cnt[p];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)cnt * d; e += (long long)gridDim.x * blockDim.x) {
+        const long long f = e / d;
+        const int k = (int)(e - f * d);
+        // Polytope(A, b) re-normalises the hull rows (polytope.py:128-138) before extreme() divides them
+        const double* row = HA + (size_t)(o + f) * d;
+        const double nrm = sqrt(np_sum_squares([&](int j) { return row[j]; }, d));
+        const double mult = __ddiv_rn(1.0, nrm);
+        const double hk = __dmul_rn(row[k], mult);
+        const double kk = __dmul_rn(Hb[o + f], mult);
+        V[(size_t)(o + f) * d + k] = __dadd_rn(__ddiv_rn(hk, kk), xc[(size_t)p * d + k]);
+    }
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" {
+
+size_t pb200_hull_workspace_bytes(int H, int Nmax, int d, int facet_cap) {
+    if (H < 0 || Nmax < 1 || d < 2 || d > HULL_MAX_D || facet_cap < d + 1) return 0;
+    const int sms = sm_count();
+    if (!sms) return 0;
+    const int grid = hull_grid(H > 0 ? H : 1);
+    return (size_t)grid * hull_ws_bytes(Nmax, d, facet_cap, hull_x_in_smem(Nmax, d)) + 256;
+}
+
+int pb200_hull_batch(const double* points, const int32_t* n_pts, int H, int Nmax, int d, double abs_tol, int facet_cap,
+                     double* out_A, double* out_b, int32_t* out_vid, long long out_cap, long long* facet_off, int32_t* facet_cnt,
+                     int32_t* status, uint8_t* is_vertex, int32_t* stats, long long* total_facets, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (H < 0 || !points || !out_A || !out_b || !out_vid || !facet_off || !facet_cnt || !status || !total_facets || !workspace)
+        return fail(PB200_EINVAL, "pb200_hull_batch: null pointer or negative batch");
+    if (d < 2 || d > HULL_MAX_D) return fail(PB200_EUNSUPPORTED, "hull: need 2 <= d <= 16");
+    if (Nmax < 1 || facet_cap < d + 1 || (long long)facet_cap * d >= (1ll << 30))
+        return fail(PB200_EUNSUPPORTED, "hull: need Nmax >= 1 and d+1 <= facet_cap, facet_cap*d < 2^30");
+    if (H == 0) return PB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = hull_grid(H);
+    if (!grid) return PB200_ECUDA;
+    const int xs = hull_x_in_smem(Nmax, d);
+    const size_t per = hull_ws_bytes(Nmax, d, facet_cap, xs);
+    if ((size_t)grid * per + 256 > workspace_bytes) return fail(PB200_EWORKSPACE, "pb200_hull_batch: workspace too small");
+    // first 256 bytes: work counter; total_facets doubles as the output-pool cursor
+    PB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    PB_CHECK_CUDA(cudaMemsetAsync(total_facets, 0, sizeof(long long), st));
+    HullArgs a;
+    a.pts = points; a.n_pts = n_pts; a.H = H; a.Nmax = Nmax; a.d = d; a.cap = facet_cap; a.tol = abs_tol;
+    a.ws = (char*)workspace + 256; a.ws_stride = per; a.x_in_smem = xs;
+    a.outA = out_A; a.outb = out_b; a.outV = out_vid; a.out_cap = out_cap;
+    a.out_used = (unsigned long long*)total_facets;
+    a.facet_off = facet_off; a.facet_cnt = facet_cnt; a.status = status; a.is_vertex = is_vertex; a.stats = stats;
+    a.next_hull = (int*)workspace;
+    const size_t smem = xs ? sizeof(double) * (size_t)Nmax * d : 0;
+    switch (d) {
+        case 2: return launch_hull<2>(a, grid, smem, st);
+        case 3: return launch_hull<3>(a, grid, smem, st);
+        case 4: return launch_hull<4>(a, grid, smem, st);
+        case 5: return launch_hull<5>(a, grid, smem, st);
+        case 6: return launch_hull<6>(a, grid, smem, st);
+        case 7: return launch_hull<7>(a, grid, smem, st);
+        case 8: return launch_hull<8>(a, grid, smem, st);
+        case 9: return launch_hull<9>(a, grid, smem, st);
+        case 10: return launch_hull<10>(a, grid, smem, st);
+        case 11: return launch_hull<11>(a, grid, smem, st);
+        case 12: return launch_hull<12>(a, grid, smem, st);
+        case 13: return launch_hull<13>(a, grid, smem, st);
+        case 14: return launch_hull<14>(a, grid, smem, st);
+        case 15: return launch_hull<15>(a, grid, smem, st);
+        default: return launch_hull<16>(a, grid, smem, st);
+    }
+}
+
+int pb200_dual_points(const double* A, const double* b, const int32_t* m_rows, const double* xc, int P, int m, int d,
+                      double* out, void* stream) {
+    if (P < 0 || !A || !b || !xc || !out) return fail(PB200_EINVAL, "pb200_dual_points: null pointer");
+    if (P == 0) return PB200_OK;
+    dual_points_kernel<<<blocks_for((long long)P * m, 256), 256, 0, (cudaStream_t)stream>>>(A, b, m_rows, xc, P, m, d, out);
+    count_launch();
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
+int pb200_dual_facets_to_vertices(const double* hull_A, const double* hull_b, const long long* facet_off,
+                                  const int32_t* facet_cnt, const double* xc, int P, int d, int max_cnt, double* V, void* stream) {
+    if (P < 0 || !hull_A || !hull_b || !facet_off || !facet_cnt || !xc || !V) return fail(PB200_EINVAL, "pb200_dual_facets_to_vertices: null pointer");
+    if (P == 0 || max_cnt <= 0) return PB200_OK;
+    if (P > 65535) return fail(PB200_EUNSUPPORTED, "dual_facets_to_vertices: at most 65535 polytopes per call");
+    unsigned gx = blocks_for((long long)max_cnt * d, 256);
+    if (gx > 1024) gx = 1024;
+    dual_facets_to_vertices_kernel<<<dim3(gx, (unsigned)P), 256, 0, (cudaStream_t)stream>>>(hull_A, hull_b, facet_off, facet_cnt, xc, P, d, V);
+    count_launch();
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
+}  // extern "C"

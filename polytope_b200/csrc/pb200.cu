@@ -19,7 +19,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "../../include/polytope_b200.h"
+#include "common.cuh"
 #include "lp_warp.cuh"
 #include "lp_warp_small.cuh"
 
@@ -28,47 +28,24 @@ namespace pb200 {
 constexpr int WPC = 4;                  // warps per CTA of the LP kernels
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
+static int g_sm_count = 0;
 
-#define PB_CHECK_CUDA(expr)                                                              \
-    do {                                                                                  \
-        cudaError_t e__ = (expr);                                                         \
-        if (e__ != cudaSuccess) {                                                         \
-            snprintf(g_err, sizeof(g_err), "%s failed: %s (%s:%d)", #expr,                \
-                     cudaGetErrorString(e__), __FILE__, __LINE__);                        \
-            return PB200_ECUDA;                                                           \
-        }                                                                                 \
-    } while (0)
-
-static int fail(int code, const char* msg) {
+int fail(int code, const char* msg) {
     snprintf(g_err, sizeof(g_err), "%s", msg);
     return code;
 }
-
-// ------------------------------------------------------------------------
-// numpy-order arithmetic.  np.sum over a contiguous axis uses pairwise
-// summation with 8 accumulators (numpy/_core/src/umath/loops_utils.h.src,
-// *_pairwise_sum); for n <= 128 that is the code below.  The reference
-// computes every row norm that way (polytope.py:129, :1094, :1285), and
-// tests/test_gpu_normalize.py checks bit-equality against numpy.
-// ------------------------------------------------------------------------
-template <class F>
-__device__ __forceinline__ double np_sum_squares(F elem, int n) {
-    if (n < 8) {
-        double res = 0.0;
-        for (int j = 0; j < n; ++j) { const double a = elem(j); res = __dadd_rn(res, __dmul_rn(a, a)); }
-        return res;
+char* err_buf(size_t* cap) { *cap = sizeof(g_err); return g_err; }
+void count_launch(int n) { g_launches += n; }
+int sm_count() {
+    if (!g_sm_count) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            g_sm_count = 0;
+            fail(PB200_ECUDA, "cannot query the SM count of the current device");
+        }
     }
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { const double a = elem(j); r[j] = __dmul_rn(a, a); }
-    int i = 8;
-    for (; i < n - (n % 8); i += 8)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const double a = elem(i + j); r[j] = __dadd_rn(r[j], __dmul_rn(a, a)); }
-    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-    for (; i < n; ++i) { const double a = elem(i); res = __dadd_rn(res, __dmul_rn(a, a)); }
-    return res;
+    return g_sm_count;
 }
 
 __device__ __forceinline__ uint64_t low_bits(int m) { return m >= 64 ? ~0ull : ((1ull << m) - 1ull); }
@@ -470,8 +447,6 @@ __global__ void __launch_bounds__(WPC * 32, PB200_SMALL_MINB) lp_kernel_small(co
     }
 }
 
-static int g_sm_count = 0;
-
 // Optional per-stage timing of pb200_reduce_batch with CUDA events recorded on
 // the launch stream (bench.py's live roofline measurement).
 constexpr int N_STAGES = 7;   // normalize, cheby, prefilter+plan, bbox, candidates, rows, finalize
@@ -492,11 +467,7 @@ template <class Kern, class Prob>
 static int launch_persistent(Kern kern, size_t smem, const Prob& prob, long long n_items, cudaStream_t st) {
     if (smem > 227 * 1024) return fail(PB200_EUNSUPPORTED, "LP too large for shared memory");
     PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (!g_sm_count) {
-        int dev = 0;
-        PB_CHECK_CUDA(cudaGetDevice(&dev));
-        PB_CHECK_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    if (!sm_count()) return PB200_ECUDA;
     int per_sm = 0;
     PB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPC * 32, smem));
     if (per_sm < 1) return fail(PB200_EUNSUPPORTED, "LP kernel does not fit on an SM");
@@ -726,8 +697,14 @@ __global__ void finalize_kernel(const double* __restrict__ bn, const uint64_t* _
     }
 }
 
-// bounding_box status conventions (polytope.py:1372-1402)
-__global__ void bbox_resolve_kernel(const int8_t* __restrict__ status, int P, int d, double* lo, double* hi) {
+// bounding_box status conventions (polytope.py:1372-1402).  An optimum that
+// sits (to 1e-13) on an axis-aligned facet +-e_j x <= b_i is returned as that
+// facet's b_i exactly: the reference's simplex returns such vertices without
+// rounding, and callers floor()/ceil() the bounds of boxes
+// (enumerate_integral_points, polytope.py:2352-2358).
+__global__ void bbox_resolve_kernel(const int8_t* __restrict__ status, const double* __restrict__ A,
+                                    const double* __restrict__ b, const int32_t* __restrict__ m_rows, int P, int m, int d,
+                                    double* lo, double* hi) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)P * d) return;
     const long long p = t / d;
@@ -736,13 +713,23 @@ __global__ void bbox_resolve_kernel(const int8_t* __restrict__ status, int P, in
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     const int8_t sl = status[p * 2 * d + j], su = status[p * 2 * d + d + j];
     double l = lo[t], u = hi[t];
+    const int mm = m_rows ? min(max(m_rows[p], 0), m) : m;
+    for (int i = 0; i < mm; ++i) {
+        const double* row = A + ((size_t)p * m + i) * d;
+        const double a = row[j];
+        if (a != 1.0 && a != -1.0) continue;
+        bool axis = true;
+        for (int k = 0; k < d; ++k) axis = axis && (k == j || row[k] == 0.0);
+        if (!axis) continue;
+        const double bi = b[(size_t)p * m + i];
+        if (a == 1.0 && su == ST_OPTIMAL && fabs(u - bi) <= 1e-13 * fmax(1.0, fabs(bi))) u = bi;
+        if (a == -1.0 && sl == ST_OPTIMAL && fabs(l + bi) <= 1e-13 * fmax(1.0, fabs(bi))) l = -bi;
+    }
     if (sl == ST_UNBOUNDED) l = -inf; else if (sl == ST_INFEASIBLE) l = 0.0; else if (sl != ST_OPTIMAL) l = nan;
     if (su == ST_UNBOUNDED) u = inf; else if (su == ST_INFEASIBLE) u = l; else if (su != ST_OPTIMAL) u = nan;
     lo[t] = l;
     hi[t] = u;
 }
-
-static inline unsigned blocks_for(long long threads, int block) { return (unsigned)((threads + block - 1) / block); }
 
 struct ReduceWorkspace {
     double *An, *bn, *bblo, *bbhi;
@@ -815,7 +802,7 @@ int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows, in
     BboxLP prob{A, b, m_rows, nullptr, nullptr, 0, m, d, 0, lo, hi, status, nullptr};
     int rc = launch_lp(prob, (long long)P * 2 * d, m, d, (cudaStream_t)stream);
     if (rc) return rc;
-    bbox_resolve_kernel<<<blocks_for((long long)P * d, 256), 256, 0, (cudaStream_t)stream>>>(status, P, d, lo, hi);
+    bbox_resolve_kernel<<<blocks_for((long long)P * d, 256), 256, 0, (cudaStream_t)stream>>>(status, A, b, m_rows, P, m, d, lo, hi);
     ++g_launches;
     PB_CHECK_CUDA(cudaGetLastError());
     return PB200_OK;

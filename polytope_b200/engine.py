@@ -204,6 +204,205 @@ def adjacent_pairs(A, b, pair_i=None, pair_j=None, abs_tol=ABS_TOL):
     return _out(host, adj, rad, status)
 
 
+# ---------------------------------------------------------------------------
+# point-set kernels
+# ---------------------------------------------------------------------------
+def contains_batch(A, b, points, m_rows=None, abs_tol=ABS_TOL, any_of=False):
+    """Polytope.contains for P stacked polytopes (polytope.py:206-218), or
+    Region.contains (:736-748) with any_of=True.
+
+    points[d, N] are column vectors, as in the reference.
+    -> bool[P, N], or bool[N] = OR over the polytopes.
+    """
+    _require_cuda()
+    lib = _capi.lib()
+    A, host = _dev(A)
+    b, _ = _dev(b)
+    pts, phost = _dev(points)
+    P, m, d = A.shape
+    assert pts.shape[0] == d, (pts.shape, d)
+    N = pts.shape[1]
+    mr, mr_ptr = _opt(m_rows, torch.int32)
+    out = torch.empty((N,) if any_of else (P, N), dtype=torch.uint8, device='cuda')
+    _capi.check(lib.pb200_contains_batch(A.data_ptr(), b.data_ptr(), mr_ptr, P, m, d, pts.data_ptr(), N,
+                                         float(abs_tol), int(bool(any_of)), out.data_ptr(), _stream()),
+                'pb200_contains_batch')
+    out = out.view(torch.bool)
+    return out.cpu().numpy() if (host and phost) else out
+
+
+def pcg64_state_words(bit_generator):
+    """(state_hi, state_lo, inc_hi, inc_lo) of a numpy PCG64 bit generator."""
+    st = bit_generator.state
+    if st.get('bit_generator') != 'PCG64':
+        raise NotImplementedError('volume(): only numpy PCG64 generators (np.random.default_rng) can be '
+                                  'regenerated on the device; got ' + str(st.get('bit_generator')))
+    s, inc = int(st['state']['state']), int(st['state']['inc'])
+    mask = (1 << 64) - 1
+    return [s >> 64, s & mask, inc >> 64, inc & mask]
+
+
+def volume_counts(A, b, lo, hi, nsamples, rng_words, m_rows=None):
+    """Monte-Carlo containment counts of volume() (polytope.py:1583-1591).
+
+    rng_words: uint64[P, 4] from pcg64_state_words, one generator per polytope.
+    -> int64[P] counts of samples strictly inside.
+    """
+    _require_cuda()
+    lib = _capi.lib()
+    A, host = _dev(A)
+    b, _ = _dev(b)
+    lo, _ = _dev(lo)
+    hi, _ = _dev(hi)
+    P, m, d = A.shape
+    words = np.ascontiguousarray(np.asarray(rng_words, dtype=np.uint64).reshape(P, 4))
+    rw = torch.from_numpy(words.view(np.int64)).to('cuda', non_blocking=True)
+    mr, mr_ptr = _opt(m_rows, torch.int32)
+    count = torch.empty(P, dtype=torch.int64, device='cuda')
+    _capi.check(lib.pb200_volume_counts(A.data_ptr(), b.data_ptr(), mr_ptr, P, m, d, lo.data_ptr(), hi.data_ptr(),
+                                        int(nsamples), rw.data_ptr(), count.data_ptr(), _stream()),
+                'pb200_volume_counts')
+    return count.cpu().numpy() if host else count
+
+
+def point_facet_sweep(points, normals, offsets, tol=ABS_TOL):
+    """quickhull's distance sweep (quickhull.py:117-121, :226-246): points[N, d]
+    against facets (normals[F, d], offsets[F]).
+    -> (first_facet int32[N], far_facet int32[N], far_dist[N])"""
+    _require_cuda()
+    lib = _capi.lib()
+    pts, host = _dev(points)
+    nrm, _ = _dev(normals)
+    off, _ = _dev(offsets)
+    N, d = pts.shape
+    F = nrm.shape[0]
+    first = torch.empty(N, dtype=torch.int32, device='cuda')
+    far = torch.empty(N, dtype=torch.int32, device='cuda')
+    dist = torch.empty(N, dtype=torch.float64, device='cuda')
+    _capi.check(lib.pb200_point_facet_sweep(pts.data_ptr(), nrm.data_ptr(), off.data_ptr(), N, F, d, float(tol),
+                                            first.data_ptr(), far.data_ptr(), dist.data_ptr(), _stream()),
+                'pb200_point_facet_sweep')
+    return _out(host, first, far, dist)
+
+
+# ---------------------------------------------------------------------------
+# convex hulls / vertex enumeration
+# ---------------------------------------------------------------------------
+HULL_OK, HULL_FEW_POINTS, HULL_FLAT, HULL_FACET_CAP, HULL_OUT_CAP, HULL_SINGULAR = range(6)
+
+
+class HullResult(object):
+    """Facets of H hulls in one pool (device tensors, or numpy if the input was host).
+
+    A[F, d], b[F]      unit outer normals and offsets, A x <= b
+    vid[F, d]          input indices of the d vertices of each simplicial facet
+    facet_off[H], facet_cnt[H]   slice of hull h in the pool
+    status[H]          HULL_*; is_vertex[H, Nmax] bool; stats[H, 2] (points inserted, facets created)
+    """
+    __slots__ = ('A', 'b', 'vid', 'facet_off', 'facet_cnt', 'status', 'is_vertex', 'stats', 'facet_cap')
+
+    def facets(self, h):
+        o, c = int(self.facet_off[h]), int(self.facet_cnt[h])
+        return self.A[o:o + c], self.b[o:o + c], self.vid[o:o + c]
+
+
+def _default_facet_cap(nmax, d):
+    if d == 2:
+        return nmax + 16
+    if d == 3:
+        return 4 * nmax + 64
+    return int(min(max(2048, 16 * nmax * d), 1 << 16))
+
+
+def hull_batch(points, n_pts=None, abs_tol=ABS_TOL, facet_cap=None, out_cap=None, max_tries=6):
+    """Convex hulls of H point sets (quickhull.py:141-359): points[H, Nmax, d].
+
+    Capacities are grown and the call repeated when a hull reports
+    HULL_FACET_CAP / HULL_OUT_CAP; anything else is returned in `status`.
+    """
+    _require_cuda()
+    lib = _capi.lib()
+    pts, host = _dev(points)
+    H, nmax, d = pts.shape
+    npt, npt_ptr = _opt(n_pts, torch.int32)
+    cap = int(facet_cap) if facet_cap else _default_facet_cap(nmax, d)
+    pool = int(out_cap) if out_cap else None
+    res = HullResult()
+    for _ in range(max_tries):
+        if pool is None:
+            pool = int(min(H * cap, max(1 << 20, (4 << 30) // (8 * (d + 1)))))
+        ws_bytes = lib.pb200_hull_workspace_bytes(H, nmax, d, cap)
+        if ws_bytes == 0:
+            raise _capi.Pb200Error('pb200_hull_workspace_bytes: unsupported sizes (need 2 <= d <= 16)')
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+        A = torch.empty((pool, d), dtype=torch.float64, device='cuda')
+        b = torch.empty(pool, dtype=torch.float64, device='cuda')
+        vid = torch.empty((pool, d), dtype=torch.int32, device='cuda')
+        off = torch.empty(H, dtype=torch.int64, device='cuda')
+        cnt = torch.empty(H, dtype=torch.int32, device='cuda')
+        status = torch.empty(H, dtype=torch.int32, device='cuda')
+        isv = torch.empty((H, nmax), dtype=torch.uint8, device='cuda')
+        stats = torch.empty((H, 2), dtype=torch.int32, device='cuda')
+        total = torch.empty(1, dtype=torch.int64, device='cuda')
+        _capi.check(lib.pb200_hull_batch(pts.data_ptr(), npt_ptr, H, nmax, d, float(abs_tol), cap, A.data_ptr(),
+                                         b.data_ptr(), vid.data_ptr(), pool, off.data_ptr(), cnt.data_ptr(),
+                                         status.data_ptr(), isv.data_ptr(), stats.data_ptr(), total.data_ptr(),
+                                         ws.data_ptr(), ws_bytes, _stream()), 'pb200_hull_batch')
+        st = status.cpu()
+        if bool((st == HULL_FACET_CAP).any()):
+            cap *= 4
+            pool = int(out_cap) if out_cap else None
+            continue
+        if bool((st == HULL_OUT_CAP).any()):
+            pool = int(total.item())
+            continue
+        break
+    else:
+        raise _capi.Pb200Error('hull_batch: capacities still too small after %d tries (facet_cap=%d)' % (max_tries, cap))
+    n_used = int(total.item())
+    outs = _out(host, A[:n_used], b[:n_used], vid[:n_used], off, cnt, status, isv.view(torch.bool), stats)
+    res.A, res.b, res.vid, res.facet_off, res.facet_cnt, res.status, res.is_vertex, res.stats = outs
+    res.facet_cap = cap
+    return res
+
+
+def dual_points(A, b, xc, m_rows=None):
+    """extreme(): Ai = A_i / (b_i - A_i . xc) (polytope.py:1659-1664) -> [P, m, d]."""
+    _require_cuda()
+    lib = _capi.lib()
+    A, host = _dev(A)
+    b, _ = _dev(b)
+    xc, _ = _dev(xc)
+    P, m, d = A.shape
+    mr, mr_ptr = _opt(m_rows, torch.int32)
+    out = torch.empty_like(A)
+    _capi.check(lib.pb200_dual_points(A.data_ptr(), b.data_ptr(), mr_ptr, xc.data_ptr(), P, m, d, out.data_ptr(),
+                                      _stream()), 'pb200_dual_points')
+    return out.cpu().numpy() if host else out
+
+
+def dual_facets_to_vertices(hull, xc):
+    """extreme(): V = H / K + xc over the facet pool of a dual hull_batch result
+    (polytope.py:1665-1676) -> V[F, d] indexed like the pool."""
+    _require_cuda()
+    lib = _capi.lib()
+    HA, host = _dev(hull.A)
+    Hb, _ = _dev(hull.b)
+    off, _ = _dev(hull.facet_off, torch.int64)
+    cnt, _ = _dev(hull.facet_cnt, torch.int32)
+    xc, _ = _dev(xc)
+    P, d = xc.shape
+    V = torch.empty_like(HA)
+    max_cnt = int(cnt.max().item()) if P else 0
+    for p0 in range(0, P, 65535):
+        p1 = min(P, p0 + 65535)
+        _capi.check(lib.pb200_dual_facets_to_vertices(HA.data_ptr(), Hb.data_ptr(), off[p0:p1].data_ptr(),
+                                                      cnt[p0:p1].data_ptr(), xc[p0:p1].data_ptr(), p1 - p0, d,
+                                                      max_cnt, V.data_ptr(), _stream()),
+                    'pb200_dual_facets_to_vertices')
+    return V.cpu().numpy() if host else V
+
+
 REDUCE_STAGES = ('normalize', 'cheby_lp', 'prefilter', 'bbox_lp', 'candidates', 'row_lp', 'finalize')
 
 

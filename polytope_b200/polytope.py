@@ -3,16 +3,19 @@
 Host-side mirror of the part of /root/reference/polytope/polytope.py that
 SURVEY.md section 8(a) puts on the hot path: the constructor normalisation and
 caches, `is_empty`, `is_fulldim`, `cheby_ball`, `bounding_box`, `reduce`,
-`Polytope.intersect`, `is_adjacent`.  Names, argument meaning, caching side
-effects and error behaviour follow the reference; every LP goes to the sm_100a
+`Polytope.intersect`, `is_adjacent`, and of the next rows of SURVEY.md 8(f):
+`contains`, `volume`, `grid_region`, `enumerate_integral_points`, `qhull`,
+`extreme`.  Names, argument meaning, caching side effects and error behaviour
+follow the reference; every LP, hull and point sweep goes to the sm_100a
 kernels through `polytope_b200.engine` (no scipy, no CPU fallback).
 
 Each single-object function has a batched sibling (`*_batch`) that runs the
 whole list in a handful of kernel launches -- that is the form the throughput
-numbers are quoted on.  Operations outside the hot path (union, diff, volume,
-projection, extreme, plotting) are not provided.
+numbers are quoted on.  Operations outside the hot path (projection, esp,
+rotation, plotting) are not provided.
 """
 import logging
+import math
 
 import numpy as np
 
@@ -77,8 +80,23 @@ class Polytope(object):
         return np.all(self.A.dot(point.flatten()) - self.b < ABS_TOL)
 
     def contains(self, points, abs_tol=ABS_TOL):
-        """Boolean array: which column vectors of `points` satisfy A x - b < abs_tol."""
-        return np.all(self.A.dot(points) - self.b[:, np.newaxis] < abs_tol, axis=0)
+        """Boolean array: which column vectors of `points` satisfy A x - b < abs_tol
+        (polytope.py:206-218), one thread per point on the device."""
+        points = np.asarray(points, dtype=float)
+        if points.ndim != 2 or self.A.size == 0:
+            return np.all(self.A.dot(points) - self.b[:, np.newaxis] < abs_tol, axis=0)
+        return engine.contains_batch(self.A[None], self.b[None], points, abs_tol=abs_tol)[0]
+
+    @property
+    def volume(self):
+        if self._volume is None:
+            self._volume = volume(self)
+        return self._volume
+
+    def _set_volume(self, polytope_volume):
+        if polytope_volume < 0.0:
+            raise ValueError('`polytope_volume` must be >= 0, given:  {v}'.format(v=polytope_volume))
+        self._volume = float(polytope_volume)
 
     def intersect(self, other, abs_tol=ABS_TOL):
         """Intersection with another Polytope (polytope.py:255-275)."""
@@ -187,10 +205,22 @@ class Region(object):
         points = np.asarray(points)
         if points.shape[0] != self.dim:
             raise ValueError('points should be column vectors')
-        contained = np.full(points.shape[1], False, dtype=bool)
-        for poly in self.list_poly:
-            contained = np.logical_or(poly.contains(points, abs_tol), contained)
-        return contained
+        if len(self.list_poly) == 0:
+            return np.full(points.shape[1], False, dtype=bool)
+        # one pass over the points for all member polytopes (polytope.py:742-747)
+        A, b, rows = _stack(self.list_poly)
+        return engine.contains_batch(A, b, np.asarray(points, dtype=float), rows, abs_tol=abs_tol, any_of=True)
+
+    @property
+    def volume(self):
+        if self._volume is None:
+            self._volume = volume(self)
+        return self._volume
+
+    def _set_volume(self, region_volume):
+        if region_volume < 0.0:
+            raise ValueError('`region_volume` must be >= 0, given:  {v}'.format(v=region_volume))
+        self._volume = float(region_volume)
 
     def __copy__(self):
         return Region(list_poly=self.list_poly[:], props=self.props.copy())
@@ -476,3 +506,242 @@ def adjacency_matrix(cells, abs_tol=ABS_TOL):
     adj[i, j] = flags
     adj[j, i] = flags
     return adj
+
+
+# ---------------------------------------------------------------------------
+# volume, grid_region, enumerate_integral_points
+# ---------------------------------------------------------------------------
+def _volume_nsamples(n, nsamples):
+    """Sample-count rule of volume() (polytope.py:1563-1582)."""
+    N = 50 if n == 1 else 500 if n == 2 else 3000 if n == 3 else 10000
+    if nsamples is not None and nsamples < 1:
+        raise ValueError('`nsamples` must be >= 1, given:  {v}'.format(v=nsamples))
+    if nsamples is not None:
+        N = nsamples
+    if N != int(N):
+        raise ValueError(('it appears that a noninteger number of samples '
+                          'has been given, namely:  {v}').format(v=nsamples))
+    return int(N)
+
+
+def volume_batch(polys, nsamples=None, seeds=None):
+    """[volume(p, nsamples, seed) for p, seed in zip(polys, seeds)] for single
+    Polytopes of one dimension: bounding boxes and the Monte-Carlo containment
+    test (polytope.py:1583-1592) each run as one launch for the whole list.  The
+    samples are numpy's `default_rng(seed).random((n, N))`, regenerated on the
+    device from the PCG64 state, so a seeded volume equals the reference's."""
+    if seeds is None:
+        seeds = [None] * len(polys)
+    out = [None] * len(polys)
+    fd = is_fulldim_batch(polys)
+    todo = [k for k, p in enumerate(polys) if fd[k]]
+    for k, p in enumerate(polys):
+        if not fd[k]:
+            out[k] = 0.0
+    if not todo:
+        return out
+    n = polys[todo[0]].A.shape[1]
+    N = _volume_nsamples(n, nsamples)
+    boxes = bounding_box_batch([polys[k] for k in todo])
+    gens = []
+    for k in todo:
+        seed = seeds[k]
+        gens.append(np.random.default_rng(seed))
+    words = [engine.pcg64_state_words(g.bit_generator) for g in gens]
+    A, b, rows = _stack([polys[k] for k in todo])
+    lo = np.array([bb[0].flatten() for bb in boxes])
+    hi = np.array([bb[1].flatten() for bb in boxes])
+    counts = engine.volume_counts(A, b, lo, hi, N, words, rows)
+    for t, k in enumerate(todo):
+        gens[t].bit_generator.advance(n * N)     # a Generator passed as `seed` ends where numpy leaves it
+        l_b, u_b = boxes[t]
+        vol = np.prod(u_b - l_b) * int(counts[t]) / N
+        polys[k]._set_volume(vol)
+        out[k] = vol
+    return out
+
+
+def volume(polyreg, nsamples=None, seed=None):
+    """Monte-Carlo volume of a Polytope or Region (polytope.py:1529-1594)."""
+    if not is_fulldim(polyreg):
+        return 0.0
+    if isinstance(polyreg, Region):
+        # the reference recurses without `nsamples` / `seed` (polytope.py:1558-1561)
+        tot_vol = 0.0
+        for v in volume_batch(polyreg.list_poly):
+            tot_vol += v
+        polyreg._set_volume(tot_vol)
+        return tot_vol
+    return volume_batch([polyreg], nsamples, [seed])[0]
+
+
+def grid_region(polyreg, res=None):
+    """Bounding-box grid points inside `polyreg` (polytope.py:2364-2399)."""
+    bbox = polyreg.bounding_box
+    if res is None:
+        density = 8
+        res = [math.ceil(density * (b[0] - a[0])) for a, b in zip(*bbox)]
+    if len(res) != polyreg.dim:
+        raise ValueError(("`len(res)` must equal the polytope's dimension "
+                          "(which is {dim}), but instead `res` is:  {res}").format(dim=polyreg.dim, res=res))
+    if any(n < 1 for n in res):
+        raise ValueError(('`res` must contain `int` values >= 1, '
+                          'instead `res` equals:  {res}').format(res=res))
+    linspaces = [np.linspace(a, b, num=n) for a, b, n in zip(*bbox, res)]
+    points = np.meshgrid(*linspaces)
+    x = np.vstack(list(map(np.ravel, points)))
+    x = x[:, polyreg.contains(x)]
+    return (x, res)
+
+
+def enumerate_integral_points(poly):
+    """All points of `poly` with integer coordinates, d x m (polytope.py:2343-2361)."""
+    a, b = poly.bounding_box
+    a_int = np.floor(a)
+    b_int = np.ceil(b)
+    intervals = list(zip(a_int.flatten(), b_int.flatten()))
+    box = box2poly(intervals)
+    res = [int(b - a + 1) for a, b in intervals]
+    grid, _ = grid_region(box, res=res)
+    inside = poly.contains(grid)
+    return grid[:, inside]
+
+
+# ---------------------------------------------------------------------------
+# SURVEY.md 8(f) rank 1: qhull, extreme
+# ---------------------------------------------------------------------------
+def qhull_batch(point_sets, abs_tol=ABS_TOL):
+    """[qhull(v, abs_tol) for v in point_sets] (same dimension) with all hulls in
+    one launch (polytope.py:1685-1695 over quickhull.py:141-359)."""
+    sets = [np.asarray(v, dtype=float) for v in point_sets]
+    out = [None] * len(sets)
+    if not sets:
+        return out
+    d = sets[0].shape[1]
+    if d < 2 or d > 16:
+        raise NotImplementedError('qhull: the B200 hull kernel covers 2 <= d <= 16, got d = %d' % d)
+    nmax = max(v.shape[0] for v in sets)
+    pts = np.zeros((len(sets), max(nmax, 1), d))
+    n_pts = np.array([v.shape[0] for v in sets], dtype=np.int32)
+    for k, v in enumerate(sets):
+        pts[k, :v.shape[0]] = v
+    res = engine.hull_batch(pts, n_pts, abs_tol=abs_tol)
+    for k, v in enumerate(sets):
+        st = int(res.status[k])
+        if st in (engine.HULL_FEW_POINTS, engine.HULL_FLAT):
+            if st == engine.HULL_FLAT:
+                print("Warning: convex hull is not fully dimensional, returning empty polytope")
+            out[k] = Polytope()
+            continue
+        if st != engine.HULL_OK:
+            raise RuntimeError('qhull: hull %d failed with status %d' % (k, st))
+        A, b, _ = res.facets(k)
+        vert = np.unique(v[res.is_vertex[k][:v.shape[0]]], axis=0)
+        out[k] = Polytope(A, b, minrep=True, vertices=vert)
+    return out
+
+
+def qhull(vertices, abs_tol=ABS_TOL):
+    """Convex hull of N x d `vertices` as a Polytope (polytope.py:1685-1695)."""
+    return qhull_batch([vertices], abs_tol)[0]
+
+
+def _extreme_low_dim(poly1):
+    """nx == 1 and nx == 2 branches of extreme() (polytope.py:1622-1653), host numpy."""
+    A = poly1.A.copy()
+    b = poly1.b.copy()
+    nc, nx = A.shape
+    V = np.array([])
+    if nx == 1:
+        for ii in range(nc):
+            V = np.append(V, b[ii] / A[ii])
+        if len(A) == 1:
+            raise Exception("extreme: polytope is unbounded")
+        return V
+    alf = np.angle(A[:, 0] + 1j * A[:, 1])
+    I = np.argsort(alf)
+    H = np.vstack([A, A[0, :]])
+    K = np.hstack([b, b[0]])
+    I = np.hstack([I, I[0]])
+    for ii in range(nc):
+        HH = np.vstack([H[I[ii], :], H[I[ii + 1], :]])
+        KK = np.hstack([K[I[ii]], K[I[ii + 1]]])
+        if np.linalg.cond(HH) == np.inf:
+            raise Exception("extreme: polytope is unbounded")
+        try:
+            v = np.linalg.solve(HH, KK)
+        except Exception:
+            raise Exception('Finding extreme points failed, Check if any unbounded Polytope is causing this.')
+        V = np.append(V, v) if len(V) == 0 else np.vstack([V, v])
+    return V
+
+
+def extreme_batch(polys):
+    """[extreme(p) for p in polys] (single Polytopes of one dimension).
+
+    reduce, Chebyshev centres, polar duals, the dual hulls and the map back to
+    vertices (polytope.py:1597-1682) each run as one launch for the whole list.
+    """
+    out = [None] * len(polys)
+    todo = []
+    for k, p in enumerate(polys):
+        if isinstance(p, Region):
+            raise Exception("extreme: not executable for regions")
+        if p.vertices is not None:
+            out[k] = p.vertices
+        else:
+            todo.append(k)
+    if not todo:
+        return out
+    reduced = reduce_batch([polys[k] for k in todo])
+    fd = is_fulldim_batch(reduced)
+    work = []
+    for t, k in enumerate(todo):
+        if not fd[t]:
+            out[k] = None
+            continue
+        nx = reduced[t].A.shape[1]
+        if nx <= 2:
+            V = _extreme_low_dim(reduced[t])
+            polys[k].vertices = V.reshape((int(V.size / nx), nx))
+            out[k] = polys[k].vertices
+        else:
+            work.append((t, k))
+    if not work:
+        return out
+    red = [reduced[t] for t, _ in work]
+    balls = cheby_ball_batch(red)
+    A, b, rows = _stack(red)
+    xc = np.array([bb[1] for bb in balls])
+    d = A.shape[2]
+    if d > 16:
+        raise NotImplementedError('extreme: the B200 hull kernel covers d <= 16, got d = %d' % d)
+    dual = engine.dual_points(A, b, xc, rows)
+    hull = engine.hull_batch(dual, rows)
+    V = engine.dual_facets_to_vertices(hull, xc)
+    for w, (t, k) in enumerate(work):
+        st = int(hull.status[w])
+        if st in (engine.HULL_FEW_POINTS, engine.HULL_FLAT):
+            out[k] = None            # qhull returned Polytope(): not full-dimensional (polytope.py:1666-1667)
+            continue
+        if st != engine.HULL_OK:
+            raise RuntimeError('extreme: dual hull %d failed with status %d' % (k, st))
+        o, c = int(hull.facet_off[w]), int(hull.facet_cnt[w])
+        # is_fulldim(Q): the dual hull contains the ball of radius min(b) around the origin
+        if not float(hull.b[o:o + c].min()) > ABS_TOL:
+            Q = Polytope(hull.A[o:o + c], hull.b[o:o + c], minrep=True)
+            if not is_fulldim(Q):
+                out[k] = None
+                continue
+        polys[k].vertices = V[o:o + c].copy()
+        out[k] = polys[k].vertices
+    return out
+
+
+def extreme(poly1):
+    """Vertices of a bounded polytope, N x d (polytope.py:1597-1682)."""
+    if poly1.vertices is not None:
+        return poly1.vertices
+    if isinstance(poly1, Region):
+        raise Exception("extreme: not executable for regions")
+    return extreme_batch([poly1])[0]

@@ -58,3 +58,25 @@ def box_grid(shape, origin=0.0, cell=1.0):
 def unit_cube3():
     """cfg1: Polytope(vstack(I3,-I3), [1,1,1,0,0,0]) (not from_box)."""
     return np.vstack([np.eye(3), -np.eye(3)]), np.array([1., 1, 1, 0, 0, 0])
+
+
+def contains_points(seed, d, n):
+    """Test points for contains(): uniform in [-1.6, 1.6]^d, a few exactly on the
+    faces of the box [-1, 1]^d and one at the origin (column vectors, d x n)."""
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1.6, 1.6, (d, n))
+    x[0, :5] = 1.0
+    x[:, 5] = 0.0
+    return x
+
+
+def hull_points(seed, n, d):
+    """Gaussian point cloud for qhull() (n x d)."""
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((n, d))
+
+
+# (m, d) / (N, d) of the golden fixtures in tests/golden/sets_cases.npz, hull_cases.npz
+VOLUME_SPECS = [(6, 2), (10, 3), (16, 4), (16, 6), (32, 8)]
+HULL_SPECS = [(20, 2), (30, 3), (40, 4), (30, 5), (24, 6)]
+EXTREME_SPECS = [(6, 2), (10, 3), (12, 4), (15, 5), (18, 6)]
