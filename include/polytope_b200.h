@@ -200,6 +200,44 @@ int pb200_dual_facets_to_vertices(const double* hull_A, const double* hull_b,
                                   const double* xc, int P, int d, int max_cnt,
                                   double* V, void* stream);
 
+/* ---- set difference -------------------------------- */
+
+/* per-problem status written by pb200_region_diff_batch */
+#define PB200_DIFF_PIECES 0       /* result = the n_pieces[t] pieces in the pool (0 pieces: Polytope()) */
+#define PB200_DIFF_UNTOUCHED 1    /* no cell intersects poly: the reference returns poly itself (:2155-2157) */
+#define PB200_DIFF_COVERED 2      /* a cell has no facet cutting poly: the reference returns Polytope() (:2183-2184) */
+#define PB200_DIFF_POOL_FULL 3    /* piece pool (or piece_m) too small: *pieces_used tells the size needed */
+#define PB200_DIFF_INDEX_ERROR 4  /* the reference would raise IndexError / sizes outside the envelope */
+#define PB200_DIFF_STEP_LIMIT 5
+
+/* T independent set differences poly_t \ region_t, each a depth-first search
+ * over Chebyshev LPs run by one warp.
+ * Replaces: region_diff(poly, reg, abs_tol, intersect_tol), polytope/polytope.py:2117-2282.
+ *   PA[T][mp][d], Pb[T][mp], p_rows[T] (nullable): the minuends, constructor-normalised
+ *   RA[T][Nr][mr][d], Rb[T][Nr][mr], r_rows[T][Nr], n_reg[T] (nullable): the cells of each
+ *     region; with reg_shared != 0 there is ONE region (leading dimension 1) used by
+ *     every problem (cfg3: 50 000 cells minus the same polytope)
+ *   piece pool (device, caller-owned): piece_A[piece_cap][piece_m][d], piece_b[..][piece_m]
+ *     raw stacked rows of each piece exactly as the reference hands them to
+ *     Polytope(A[INDICES], B[INDICES]); piece_rows = row count; piece_reduce = 1 when the
+ *     reference passes the piece through reduce() (:2276); piece_owner = t; piece_seq =
+ *     position in the reference's union order
+ *   pieces_used (device, 1 value): pieces appended (also beyond piece_cap)
+ *   status[T] PB200_DIFF_*, n_pieces[T], n_lp[T] (LPs solved for problem t)
+ *   work_counter: 4 bytes of device scratch.
+ * Limits: every LP of a search (rows of poly + rows of the cells cutting it) <= 128 rows,
+ * else that problem ends with PB200_DIFF_INDEX_ERROR; Nr <= 64, Nr * mr <= 2048, d <= 31.
+ * piece_m = min(128, mp + 2 * Nr * mr) is always enough. */
+int pb200_region_diff_batch(const double* PA, const double* Pb, const int32_t* p_rows,
+                            int T, int mp, int d, const double* RA, const double* Rb,
+                            const int32_t* r_rows, const int32_t* n_reg, int reg_shared,
+                            int Nr, int mr, double abs_tol, double intersect_tol,
+                            double* piece_A, double* piece_b, int32_t* piece_rows,
+                            int32_t* piece_reduce, int32_t* piece_owner, int32_t* piece_seq,
+                            long long piece_cap, int piece_m, long long* pieces_used,
+                            int32_t* status, int32_t* n_pieces, int32_t* n_lp,
+                            int* work_counter, void* stream);
+
 /* Per-stage device times of the last pb200_reduce_batch call made while
  * profiling was enabled: CUDA events recorded on the launch stream around the
  * 7 stages (normalize, cheby LP, prefilter, bbox LPs, candidates, row LPs,

@@ -389,3 +389,152 @@ def extreme(A, b):
     if len(H) == 0:
         return None
     return H / K[:, None] + xmid
+
+
+# ---------------------------------------------------------------------------
+# envelope, region_diff
+# ---------------------------------------------------------------------------
+def cheby_radius_of_rows(A, b):
+    """cheby_ball(Polytope(A, b))[0]: constructor normalisation, then the LP."""
+    An, bn, _ = normalize_rows(A, b)
+    return cheby_ball(An, bn)[0]
+
+
+def envelope_outer_rows(cells, abs_tol=ABS_TOL):
+    """The 'outer' rows of envelope(), polytope.py:1430-1458: for every cell i the
+    indices of its rows that no other cell crosses.  `cells` = list of (A, b)."""
+    out = []
+    for i, (A1, b1) in enumerate(cells):
+        outer = np.ones(A1.shape[0])
+        for ii in range(A1.shape[0]):
+            for j, (A2, b2) in enumerate(cells):
+                if i == j:
+                    continue
+                rc = cheby_radius_of_rows(np.vstack([A2, -A1[ii, :]]), np.hstack([b2, -b1[ii]]))
+                if rc > abs_tol:
+                    outer[ii] = 0
+        out.append(np.nonzero(outer)[0])
+    return out
+
+
+def envelope(cells, abs_tol=ABS_TOL):
+    """envelope() of a region given as normalised cells, polytope.py:1414-1464.
+    Returns the `reduce` dict of the stacked outer rows (empty=True when the
+    reference returns Polytope())."""
+    outer = envelope_outer_rows(cells, abs_tol)
+    Ae = np.vstack([A[idx, :] for (A, b), idx in zip(cells, outer)])
+    be = np.hstack([b[idx] for (A, b), idx in zip(cells, outer)])
+    if len(be) == 0:
+        return dict(empty=True, keep=[], A=None, b=None)
+    red = reduce(Ae, be, abs_tol=abs_tol)
+    if not red['empty']:
+        Ar, br, _ = normalize_rows(red['A'], red['b'])
+        if not is_fulldim(Ar, br):
+            red['empty'] = True
+    return red
+
+
+class _PyList(list):
+    """INDICES of region_diff: numpy fancy indexing wraps negative entries."""
+
+
+def region_diff(poly, cells, abs_tol=ABS_TOL, intersect_tol=ABS_TOL, max_steps=100000):
+    """region_diff(poly, reg), polytope.py:2117-2282, on normalised (A, b) pairs.
+
+    Returns (kind, pieces):
+      kind 'poly'    -- the reference returns `poly` itself (no cell intersects it)
+      kind 'empty'   -- the reference returns Polytope() (a cell covers poly)
+      kind 'pieces'  -- pieces = [(A_rows, b_rows, reduced)] in the order the
+                        reference unions them; `reduced` pieces went through
+                        reduce() (:2276), the others are used as they are (:2217).
+                        Rows are the RAW stacked rows handed to Polytope(...).
+    """
+    PA, Pb = poly
+    N = len(cells)
+    Rc = np.zeros(N)
+    for i, (A1, b1) in enumerate(cells):
+        Rc[i] = cheby_radius_of_rows(np.vstack([PA, A1]), np.hstack([Pb, b1]))
+    N = int(np.sum(Rc >= intersect_tol))
+    if N == 0:
+        return 'poly', []
+    ind = np.argsort(-Rc)
+    A = PA.copy()
+    B = Pb.copy()
+    m = A.shape[0]
+    mi = np.zeros(N, dtype=int)
+    HK = np.hstack([A, np.array([B]).T])
+    for ii in range(N):
+        i = ind[ii]
+        if not is_fulldim(*cells[i]):
+            continue
+        Hni, Kni = cells[i]
+        for j in range(Hni.shape[0]):
+            HKnij = np.hstack([Hni[j, :], Kni[j]])
+            if np.all(np.sum(np.abs(HK - np.tile(HKnij, [m, 1])), axis=1) >= abs_tol):
+                mi[ii] += 1
+                A = np.vstack([A, Hni[j, :]])
+                B = np.hstack([B, Kni[j]])
+    if np.any(mi == 0):
+        return 'empty', []
+    M = int(np.sum(mi))
+    beg_mi = np.cumsum(np.hstack([0, mi[:-1]])) + m if N > 1 else np.array([m])
+    A = np.vstack([A, -A[m:m + M, :]])
+    B = np.hstack([B, -B[m:m + M]])
+    counter = np.zeros(N, dtype=int)
+    INDICES = list(range(m))
+    level = 0
+    pieces = []
+
+    def radius(idx):
+        idx = np.array(idx, dtype=int)
+        return cheby_radius_of_rows(A[idx, :], B[idx])
+
+    for _ in range(max_steps):
+        if level == -1:
+            break
+        if counter[level] == 0:
+            for j in range(level, N):
+                R = radius(INDICES + list(range(beg_mi[j], beg_mi[j] + mi[j])))
+                if R > abs_tol:
+                    level = j
+                    counter[level] = 1
+                    INDICES = INDICES + [beg_mi[level] + M]
+                    break
+            if R < abs_tol:
+                level = level - 1
+                idx = np.array(INDICES, dtype=int)
+                pieces.append((A[idx, :], B[idx], False))
+                nz = len(np.nonzero(counter)[0])
+                for _jj in range(nz - 1, -1, -1):
+                    if counter[level] <= mi[level]:
+                        INDICES[-1] = INDICES[-1] - M
+                        INDICES = INDICES + [beg_mi[level] + counter[level] + M]
+                        break
+                    else:
+                        counter[level] = 0
+                        INDICES = INDICES[0:m + int(np.sum(counter))]
+                        if level == -1:
+                            return 'pieces', pieces
+        else:
+            nzcount = np.nonzero(counter)[0]
+            for jj in range(len(nzcount) - 1, -1, -1):
+                level = nzcount[jj]
+                counter[level] += 1
+                if counter[level] <= mi[level]:
+                    INDICES[-1] = INDICES[-1] - M
+                    INDICES = INDICES + [beg_mi[level] + counter[level] + M - 1]
+                    break
+                else:
+                    counter[level] = 0
+                    INDICES = INDICES[0:m + int(np.sum(counter))]
+                    level = level - 1
+                    if level == -1:
+                        return 'pieces', pieces
+        idx = np.array(INDICES, dtype=int)
+        rc = cheby_radius_of_rows(A[idx, :], B[idx])
+        if rc > abs_tol:
+            if level == N - 1:
+                pieces.append((A[idx, :], B[idx], True))
+            else:
+                level = level + 1
+    return 'pieces', pieces

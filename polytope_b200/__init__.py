@@ -14,6 +14,7 @@ from polytope_b200.polytope import (
     cheby_ball_batch, is_fulldim_batch, bounding_box_batch, reduce_batch,
     intersect_batch, adjacency_matrix,
     volume, volume_batch, grid_region, enumerate_integral_points,
-    qhull, qhull_batch, extreme, extreme_batch)
+    qhull, qhull_batch, extreme, extreme_batch,
+    envelope, is_convex, is_subset, union, region_diff, region_diff_batch, mldivide)
 
 __version__ = '0.1.0'

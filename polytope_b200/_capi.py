@@ -38,6 +38,9 @@ SIGNATURES = {
                          + [c_longlong] + [c_void_p] * 7 + [c_size_t, c_void_p]),
     'pb200_dual_points': (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 2),
     'pb200_dual_facets_to_vertices': (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p] * 2),
+    'pb200_region_diff_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p] * 4 + [c_int] * 3
+                                + [c_double] * 2 + [c_void_p] * 6 + [c_longlong, c_int] + [c_void_p] * 5
+                                + [c_void_p]),
     'pb200_adjacent_pairs': (c_int, [c_void_p] * 2 + [c_int] * 3 + [c_void_p] * 2
                              + [c_longlong, c_double] + [c_void_p] * 4),
 }

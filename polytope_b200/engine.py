@@ -403,6 +403,79 @@ def dual_facets_to_vertices(hull, xc):
     return V.cpu().numpy() if host else V
 
 
+# ---------------------------------------------------------------------------
+# set difference
+# ---------------------------------------------------------------------------
+DIFF_PIECES, DIFF_UNTOUCHED, DIFF_COVERED, DIFF_POOL_FULL, DIFF_INDEX_ERROR, DIFF_STEP_LIMIT = range(6)
+
+
+class DiffResult(object):
+    """Pieces of T set differences (device tensors, or numpy if the input was host).
+
+    status[T], n_pieces[T], n_lp[T]; the pool is sorted by (owner, seq):
+    piece_off[T] = first piece of problem t; A[F, piece_m, d], b[F, piece_m],
+    rows[F], reduce[F] (the reference passes this piece through reduce()).
+    """
+    __slots__ = ('status', 'n_pieces', 'n_lp', 'piece_off', 'A', 'b', 'rows', 'reduce', 'owner')
+
+
+def region_diff_batch(PA, Pb, RA, Rb, p_rows=None, r_rows=None, n_reg=None, abs_tol=ABS_TOL,
+                      intersect_tol=ABS_TOL, piece_cap=None, max_tries=4):
+    """poly_t \\ region_t for T problems (polytope.py:2117-2282).
+
+    PA[T, mp, d], Pb[T, mp]; RA[T, Nr, mr, d], Rb[T, Nr, mr] -- or RA[Nr, mr, d],
+    Rb[Nr, mr] for one region shared by all problems.
+    """
+    _require_cuda()
+    lib = _capi.lib()
+    PA, host = _dev(PA)
+    Pb, _ = _dev(Pb)
+    RA, _ = _dev(RA)
+    Rb, _ = _dev(Rb)
+    T, mp, d = PA.shape
+    shared = RA.dim() == 3
+    Nr, mr = (RA.shape[0], RA.shape[1]) if shared else (RA.shape[1], RA.shape[2])
+    pr, pr_ptr = _opt(p_rows, torch.int32)
+    rr, rr_ptr = _opt(r_rows, torch.int32)
+    nr, nr_ptr = _opt(n_reg, torch.int32)
+    piece_m = min(128, mp + 2 * Nr * mr)
+    cap = int(piece_cap) if piece_cap else max(4 * T, 1024)
+    status = torch.empty(T, dtype=torch.int32, device='cuda')
+    npieces = torch.empty(T, dtype=torch.int32, device='cuda')
+    nlp = torch.empty(T, dtype=torch.int32, device='cuda')
+    used = torch.empty(1, dtype=torch.int64, device='cuda')
+    counter = torch.empty(1, dtype=torch.int32, device='cuda')
+    for _ in range(max_tries):
+        pA = torch.empty((cap, piece_m, d), dtype=torch.float64, device='cuda')
+        pb = torch.empty((cap, piece_m), dtype=torch.float64, device='cuda')
+        prow = torch.empty(cap, dtype=torch.int32, device='cuda')
+        pred = torch.empty(cap, dtype=torch.int32, device='cuda')
+        pown = torch.empty(cap, dtype=torch.int32, device='cuda')
+        pseq = torch.empty(cap, dtype=torch.int32, device='cuda')
+        _capi.check(lib.pb200_region_diff_batch(
+            PA.data_ptr(), Pb.data_ptr(), pr_ptr, T, mp, d, RA.data_ptr(), Rb.data_ptr(), rr_ptr, nr_ptr,
+            int(shared), Nr, mr, float(abs_tol), float(intersect_tol), pA.data_ptr(), pb.data_ptr(),
+            prow.data_ptr(), pred.data_ptr(), pown.data_ptr(), pseq.data_ptr(), cap, piece_m, used.data_ptr(),
+            status.data_ptr(), npieces.data_ptr(), nlp.data_ptr(), counter.data_ptr(), _stream()),
+            'pb200_region_diff_batch')
+        n_used = int(used.item())
+        if n_used <= cap:
+            break
+        cap = n_used
+    else:
+        raise _capi.Pb200Error('region_diff_batch: piece pool still too small')
+    # pool order is arrival order: sort by (owner, seq)
+    key = pown[:n_used].to(torch.int64) * (1 << 31) + pseq[:n_used].to(torch.int64)
+    order = torch.argsort(key)
+    res = DiffResult()
+    ok_pieces = torch.where(status == DIFF_POOL_FULL, torch.zeros_like(npieces), npieces)
+    off = torch.cumsum(ok_pieces.to(torch.int64), 0) - ok_pieces.to(torch.int64)
+    outs = _out(host, status, npieces, nlp, off, pA[:n_used][order], pb[:n_used][order], prow[:n_used][order],
+                pred[:n_used][order], pown[:n_used][order])
+    (res.status, res.n_pieces, res.n_lp, res.piece_off, res.A, res.b, res.rows, res.reduce, res.owner) = outs
+    return res
+
+
 REDUCE_STAGES = ('normalize', 'cheby_lp', 'prefilter', 'bbox_lp', 'candidates', 'row_lp', 'finalize')
 
 

@@ -100,6 +100,8 @@ class Polytope(object):
 
     def intersect(self, other, abs_tol=ABS_TOL):
         """Intersection with another Polytope (polytope.py:255-275)."""
+        if isinstance(other, Region):
+            return other.intersect(self, abs_tol=abs_tol)
         if not isinstance(other, Polytope):
             raise Exception('Polytope intersection defined only with other Polytope. '
                             'Got instead: ' + str(type(other)))
@@ -110,6 +112,31 @@ class Polytope(object):
         iA = np.vstack([self.A, other.A])
         ib = np.hstack([self.b, other.b])
         return reduce(Polytope(iA, ib), abs_tol=abs_tol)
+
+    def __eq__(self, other):
+        return self <= other and other <= self
+
+    def __ne__(self, other):
+        return not self == other
+
+    def __le__(self, other):
+        return is_subset(self, other)
+
+    def __ge__(self, other):
+        return is_subset(other, self)
+
+    __hash__ = object.__hash__
+
+    def __bool__(self):
+        return bool(self.volume > 0)
+
+    __nonzero__ = __bool__
+
+    def union(self, other, check_convex=False):
+        return union(self, other, check_convex)
+
+    def diff(self, other):
+        return mldivide(self, other)
 
     @classmethod
     def from_box(cls, intervals=[]):
@@ -221,6 +248,58 @@ class Region(object):
         if region_volume < 0.0:
             raise ValueError('`region_volume` must be >= 0, given:  {v}'.format(v=region_volume))
         self._volume = float(region_volume)
+
+    def __eq__(self, other):
+        return self <= other and other <= self
+
+    def __ne__(self, other):
+        return not self == other
+
+    def __le__(self, other):
+        return is_subset(self, other)
+
+    def __ge__(self, other):
+        return is_subset(other, self)
+
+    __hash__ = object.__hash__
+
+    def __add__(self, other):
+        """Union with convex simplification (polytope.py:762-775)."""
+        return union(self, other, check_convex=True)
+
+    def __bool__(self):
+        return bool(self.volume > 0)
+
+    __nonzero__ = __bool__
+
+    def union(self, other, check_convex=False):
+        return union(self, other, check_convex)
+
+    def __sub__(self, other):
+        return mldivide(self, other)
+
+    def diff(self, other):
+        return mldivide(self, other)
+
+    def __and__(self, other):
+        return intersect(self, other)
+
+    def intersect(self, other, abs_tol=ABS_TOL):
+        """Intersection with a Polytope or an iterable of Polytopes (polytope.py:815-830):
+        all pairwise intersections in one device pass, then the reference's union
+        accumulation."""
+        if isinstance(other, Polytope):
+            other = [other]
+        pairs = [(poly0, poly1) for poly0 in self for poly1 in other]
+        P = Region()
+        if not pairs:
+            return P
+        isects = intersect_batch([a for a, _ in pairs], [b for _, b in pairs], abs_tol)
+        balls = cheby_ball_batch(isects)
+        for isect, (rp, _) in zip(isects, balls):
+            if rp > abs_tol:
+                P = union(P, isect, check_convex=True)
+        return P
 
     def __copy__(self):
         return Region(list_poly=self.list_poly[:], props=self.props.copy())
@@ -438,7 +517,13 @@ def reduce(poly, nonEmptyBounded=1, abs_tol=ABS_TOL):
 
 
 def intersect(poly1, poly2, abs_tol=ABS_TOL):
-    """poly1 & poly2 for two Polytopes (polytope.py:1508-1526)."""
+    """Intersection of two polytopes or regions (polytope.py:1508-1526)."""
+    if isinstance(poly1, Region):
+        return poly1.intersect(poly2, abs_tol=abs_tol)
+    if isinstance(poly2, Region):
+        return poly2.intersect(poly1, abs_tol=abs_tol)
+    if not isinstance(poly1, Polytope):
+        raise Exception('poly1 not Region nor Polytope.Got instead: ' + str(type(poly1)))
     return poly1.intersect(poly2, abs_tol)
 
 
@@ -745,3 +830,224 @@ def extreme(poly1):
     if isinstance(poly1, Region):
         raise Exception("extreme: not executable for regions")
     return extreme_batch([poly1])[0]
+
+
+# ---------------------------------------------------------------------------
+# envelope, is_convex, union, region_diff, mldivide
+# ---------------------------------------------------------------------------
+def envelope(reg, abs_tol=ABS_TOL):
+    """Envelope of a region (polytope.py:1414-1464): the nP (nP-1) m Chebyshev LPs
+    "does cell j cross facet ii of cell i" are independent and run as one batch."""
+    cells = reg.list_poly
+    nP = len(cells)
+    jobs = []           # (i, ii, j)
+    for i in range(nP):
+        for ii in range(cells[i].A.shape[0]):
+            for j in range(nP):
+                if i != j:
+                    jobs.append((i, ii, j))
+    outer = [np.ones(c.A.shape[0]) for c in cells]
+    if jobs:
+        tests = [Polytope(np.vstack([cells[j].A, -cells[i].A[ii, :]]), np.hstack([cells[j].b, -cells[i].b[ii]]))
+                 for i, ii, j in jobs]
+        for (i, ii, j), (rc, _) in zip(jobs, cheby_ball_batch(tests)):
+            if rc > abs_tol:
+                outer[i][ii] = 0
+    Ae = np.vstack([c.A[np.nonzero(o)[0], :] for c, o in zip(cells, outer)])
+    be = np.hstack([c.b[np.nonzero(o)[0]] for c, o in zip(cells, outer)])
+    ret = reduce(Polytope(Ae, be), abs_tol=abs_tol)
+    if is_fulldim(ret):
+        return ret
+    return Polytope()
+
+
+def is_convex(reg, abs_tol=ABS_TOL):
+    """(convex?, envelope or None) for a region (polytope.py:988-1014)."""
+    if len(reg) == 0:
+        return True, None
+    outer = envelope(reg)
+    if is_empty(outer):
+        return False, None
+    Pl, Pu = reg.bounding_box
+    Ol, Ou = outer.bounding_box
+    bboxP = np.hstack([Pl, Pu])
+    bboxO = np.hstack([Ol, Ou])
+    if (np.any(abs(bboxP[:, 0] - bboxO[:, 0]) > abs_tol) or
+            np.any(abs(bboxP[:, 1] - bboxO[:, 1]) > abs_tol)):
+        return False, None
+    if is_fulldim(outer.diff(reg)):
+        return False, None
+    return True, outer
+
+
+def is_subset(small, big, abs_tol=ABS_TOL):
+    """small is a subset of big, by the volume of the difference (polytope.py:1034-1052)."""
+    for x in [small, big]:
+        if not isinstance(x, (Polytope, Region)):
+            raise TypeError('Not a Polytope or Region, got instead:\n\t' + str(type(x)))
+    diff = small.diff(big)
+    return bool(diff.volume < abs_tol)
+
+
+def union(polyreg1, polyreg2, check_convex=False):
+    """Union of polytopes / regions as a Region of non-overlapping polytopes
+    (polytope.py:1166-1238)."""
+    if is_empty(polyreg1):
+        return polyreg2
+    if is_empty(polyreg2):
+        return polyreg1
+    if check_convex:
+        s1 = intersect(polyreg1, polyreg2)
+        if is_fulldim(s1):
+            s2 = polyreg2.diff(polyreg1)
+            s3 = polyreg1.diff(polyreg2)
+        else:
+            s2 = polyreg1
+            s3 = polyreg2
+    else:
+        s1 = polyreg1
+        s2 = polyreg2
+        s3 = None
+    lst = []
+    for part in (s1, s2, s3):
+        if part is None:
+            continue
+        if len(part) == 0:
+            if not is_empty(part):
+                lst.append(part)
+        else:
+            for poly in part.list_poly:
+                if not is_empty(poly):
+                    lst.append(poly)
+    if check_convex:
+        final = []
+        N = len(lst)
+        if N > 1:
+            while N > 0:
+                templist = [lst[0]]
+                for ii in range(1, N):
+                    templist.append(lst[ii])
+                    is_conv, env = is_convex(Region(templist))
+                    if not is_conv:
+                        templist.remove(lst[ii])
+                for poly in templist:
+                    lst.remove(poly)
+                cvxpoly = reduce(envelope(Region(templist)))
+                if not is_empty(cvxpoly):
+                    final.append(reduce(cvxpoly))
+                N = len(lst)
+        else:
+            final = lst
+        return Region(final)
+    return Region(lst)
+
+
+def region_diff_batch(polys, regs, abs_tol=ABS_TOL, intersect_tol=ABS_TOL):
+    """[region_diff(p, r) for p, r in zip(polys, regs)] with every depth-first
+    search running on its own warp (polytope.py:2117-2282).  `regs` may be one
+    Region / Polytope shared by all minuends."""
+    if isinstance(regs, (Polytope, Region)):
+        regs = [regs] * len(polys)
+    out = [None] * len(polys)
+    todo, cells_of = [], []
+    for k, (poly, reg) in enumerate(zip(polys, regs)):
+        if not isinstance(poly, Polytope):
+            raise Exception('poly not a Polytope, but: ' + str(type(poly)))
+        if isinstance(reg, Polytope):
+            reg = Region([reg])
+        if not isinstance(reg, Region):
+            raise Exception('reg not a Region, but: ' + str(type(reg)))
+        if is_empty(reg):
+            out[k] = poly.copy()
+        elif is_empty(poly):
+            out[k] = Polytope()
+        else:
+            todo.append(k)
+            cells_of.append(reg.list_poly)
+    if not todo:
+        return out
+    PA, Pb, prow = _stack([polys[k] for k in todo])
+    shared = all(c is cells_of[0] for c in cells_of)
+    groups = [cells_of[0]] if shared else cells_of
+    Nr = max(len(c) for c in groups)
+    d = PA.shape[2]
+    mr = max(max(p.A.shape[0] for p in c) for c in groups)
+    RA = np.zeros((len(groups), Nr, mr, d))
+    Rb = np.zeros((len(groups), Nr, mr))
+    rrow = np.zeros((len(groups), Nr), dtype=np.int32)
+    nreg = np.array([len(c) for c in groups], dtype=np.int32)
+    for g, c in enumerate(groups):
+        for i, p in enumerate(c):
+            rrow[g, i] = p.A.shape[0]
+            RA[g, i, :rrow[g, i]] = p.A
+            Rb[g, i, :rrow[g, i]] = p.b
+    if shared:
+        RA, Rb = RA[0], Rb[0]
+    res = engine.region_diff_batch(PA, Pb, RA, Rb, prow, rrow, nreg, abs_tol, intersect_tol)
+    # pieces the reference reduces: one device pass for all of them
+    red_idx = np.nonzero(res.reduce)[0]
+    reduced = {}
+    if len(red_idx):
+        mx = int(res.rows[red_idx].max())          # the pool is padded to piece_m rows
+        rr = engine.reduce_batch(np.ascontiguousarray(res.A[red_idx][:, :mx]), np.ascontiguousarray(res.b[red_idx][:, :mx]),
+                                 res.rows[red_idx], normalize=True)
+        keeps = rr.keep_lists()
+        for t, f in enumerate(red_idx):
+            if rr.flags[t] & engine.F_EMPTY:
+                reduced[f] = Polytope()
+            else:
+                q = Polytope(rr.A[t][keeps[t]], rr.b[t][keeps[t]])
+                q.minrep = bool(rr.flags[t] & engine.F_MINREP)
+                reduced[f] = q
+    for t, k in enumerate(todo):
+        st = int(res.status[t])
+        if st == engine.DIFF_UNTOUCHED:
+            out[k] = polys[k].copy()
+        elif st == engine.DIFF_COVERED:
+            out[k] = Polytope()
+        elif st == engine.DIFF_PIECES:
+            acc = Polytope()
+            o = int(res.piece_off[t])
+            for f in range(o, o + int(res.n_pieces[t])):
+                if res.reduce[f]:
+                    piece = reduced[f]
+                else:
+                    n = int(res.rows[f])
+                    piece = Polytope(res.A[f][:n], res.b[f][:n])
+                acc = union(acc, piece, False)
+            out[k] = acc
+        elif st == engine.DIFF_INDEX_ERROR:
+            raise IndexError('region_diff: problem %d is outside the kernel envelope '
+                             '(rows per LP <= 128, <= 64 cells) or indexes past the stacked rows' % k)
+        else:
+            raise RuntimeError('region_diff: problem %d ended with status %d' % (k, st))
+    return out
+
+
+def region_diff(poly, reg, abs_tol=ABS_TOL, intersect_tol=ABS_TOL, save=False):
+    """poly minus reg (polytope.py:2117-2282)."""
+    if not isinstance(poly, Polytope):
+        raise Exception('poly not a Polytope, but: ' + str(type(poly)))
+    if isinstance(reg, Polytope):
+        reg = Region([reg])
+    if not isinstance(reg, Region):
+        raise Exception('reg not a Region, but: ' + str(type(reg)))
+    return region_diff_batch([poly], [reg], abs_tol, intersect_tol)[0]
+
+
+def mldivide(a, b, save=False):
+    """Set difference a minus b (polytope.py:1469-1505)."""
+    if isinstance(b, Polytope):
+        b = Region([b])
+    if isinstance(a, Region):
+        P = Region()
+        for poly in a:
+            Pdiff = poly
+            for poly1 in b:
+                Pdiff = mldivide(Pdiff, poly1, save=save)
+            P = union(P, Pdiff, check_convex=True)
+    elif isinstance(a, Polytope):
+        P = region_diff(a, b)
+    else:
+        raise Exception('a neither Region nor Polytope')
+    return P

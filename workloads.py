@@ -80,3 +80,36 @@ def hull_points(seed, n, d):
 VOLUME_SPECS = [(6, 2), (10, 3), (16, 4), (16, 6), (32, 8)]
 HULL_SPECS = [(20, 2), (30, 3), (40, 4), (30, 5), (24, 6)]
 EXTREME_SPECS = [(6, 2), (10, 3), (12, 4), (15, 5), (18, 6)]
+
+
+def diff_case(i):
+    """Seeded (poly, [cells]) inputs for region_diff / envelope / union tests:
+    raw (A, b) pairs.  d cycles 2, 3, 4; the cells are shifted copies of box+cuts
+    polytopes so that some intersect the minuend, some cover it, some miss it."""
+    d = 2 + i % 3
+    m = 2 * d + 2 + (i % 2)
+    rng = np.random.default_rng(5000 + i)
+    A, b = box_cuts(5100 + i, m, d)
+    ncell = 1 + i % 3
+    cells = []
+    for c in range(ncell):
+        Ac, bc = box_cuts(5200 + 10 * i + c, m, d)
+        kind = (i + c) % 5
+        if kind == 4:
+            shift, scale = np.zeros(d), 3.0                  # covers the minuend
+        elif kind == 3:
+            shift, scale = 4.0 * np.ones(d), 1.0             # misses it
+        else:
+            shift, scale = rng.uniform(-1.2, 1.2, d), rng.uniform(0.5, 1.3)
+        cells.append((Ac, scale * bc + Ac @ shift))
+    return (A, b), cells
+
+
+def box_rows(intervals):
+    """Rows [I; -I] x <= [hi; -lo] of a hyperrectangle (what box2poly builds)."""
+    iv = np.asarray(intervals, dtype=float)
+    n = iv.shape[0]
+    return np.vstack([np.eye(n), -np.eye(n)]), np.hstack([iv[:, 1], -iv[:, 0]])
+
+
+DIFF_CASES = 30
