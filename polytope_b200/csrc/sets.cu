@@ -57,78 +57,148 @@ __device__ __forceinline__ double pcg_next_double(u128& s, u128 inc) {
     return (double)(u >> 11) * (1.0 / 9007199254740992.0);
 }
 
-// rows of one polytope against a point held in registers; `strict_tol`:
-// contains() tests  A x - b < abs_tol,  volume() tests  A x - b < 0
-template <int D>
-__device__ __forceinline__ bool inside_rows(const double* __restrict__ As, const double* __restrict__ bs, int mm, int d,
-                                            const double (&x)[D > 0 ? D : 32], double tol) {
-    bool ok = true;
-    for (int i = 0; i < mm && ok; ++i) {
-        double acc = 0.0;
-        if (D > 0) {
+// Rows of one polytope against TWO points held in registers.  The rows sit in
+// shared memory with an even leading dimension DP (a zero pad column when d is
+// odd) so that one 128-bit broadcast load feeds four DFMAs (2 columns x 2
+// points); four rows are in flight per step (independent fma chains).
+// contains() tests  A x - b < abs_tol,  volume() tests  A x - b < 0.
+// The sums are acc = fma(A[i][k], x[k], acc) in k order -- what numpy's dgemm
+// computes; the pad column adds fma(0, 0, acc) = acc.
+template <int DP>
+__device__ __forceinline__ void inside_rows_x2(const double* __restrict__ As, const double* __restrict__ bs, int mm,
+                                               const double (&x0)[DP], const double (&x1)[DP], double tol, bool& in0, bool& in1) {
+    constexpr int R = 4;
+    bool ok0 = true, ok1 = true;
+    int i = 0;
+    for (; i + R <= mm && (ok0 || ok1); i += R) {
+        double a0[R], a1[R];
 #pragma unroll
-            for (int k = 0; k < (D > 0 ? D : 1); ++k) acc = fma(As[i * D + k], x[k], acc);
-        } else {
-            for (int k = 0; k < d; ++k) acc = fma(As[i * d + k], x[k], acc);
+        for (int r = 0; r < R; ++r) { a0[r] = 0.0; a1[r] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < DP; k += 2)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double2 g = *reinterpret_cast<const double2*>(As + (i + r) * DP + k);
+                a0[r] = fma(g.x, x0[k], a0[r]);
+                a1[r] = fma(g.x, x1[k], a1[r]);
+                a0[r] = fma(g.y, x0[k + 1], a0[r]);
+                a1[r] = fma(g.y, x1[k + 1], a1[r]);
+            }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double bi = bs[i + r];
+            ok0 = ok0 && (__dsub_rn(a0[r], bi) < tol);
+            ok1 = ok1 && (__dsub_rn(a1[r], bi) < tol);
         }
-        ok = __dsub_rn(acc, bs[i]) < tol;
     }
-    return ok;
+    for (; i < mm && (ok0 || ok1); ++i) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; k += 2) {
+            const double2 g = *reinterpret_cast<const double2*>(As + i * DP + k);
+            a0 = fma(g.x, x0[k], a0);
+            a1 = fma(g.x, x1[k], a1);
+            a0 = fma(g.y, x0[k + 1], a0);
+            a1 = fma(g.y, x1[k + 1], a1);
+        }
+        const double bi = bs[i];
+        ok0 = ok0 && (__dsub_rn(a0, bi) < tol);
+        ok1 = ok1 && (__dsub_rn(a1, bi) < tol);
+    }
+    in0 = ok0;
+    in1 = ok1;
 }
 
 // ------------------------------------------------------------------------
-// contains: P polytopes x N points.  One thread per point, the polytopes are
-// walked in shared-memory chunks.  mode 0: out[P][N]; mode 1: out[N] = OR over p.
+// contains: P polytopes x N points.  One thread per PAIR of points of a
+// 512-point tile: adjacent points (2t, 2t+1) fetched with one 128-bit streaming
+// load per coordinate when N is even (VEC), else (t, t + 256) with 64-bit loads.
+// The polytopes are walked in shared-memory chunks (staged once when they all
+// fit).  mode 0: out[P][N]; mode 1: out[N] = OR over p.
 // ------------------------------------------------------------------------
 constexpr int SET_THREADS = 256;
 constexpr int CHUNK_DOUBLES = 4096;      // 32 KB of staged rows per chunk
 
-template <int D>
+template <int D, bool VEC>
 __global__ void __launch_bounds__(SET_THREADS) contains_kernel(const double* __restrict__ A, const double* __restrict__ b,
                                                                const int32_t* __restrict__ m_rows, int P, int m, int d,
                                                                const double* __restrict__ pts, long long N, double abs_tol,
                                                                int mode, uint8_t* __restrict__ out, int polys_per_chunk) {
-    __shared__ double sh[CHUNK_DOUBLES];
+    __shared__ __align__(16) double sh[CHUNK_DOUBLES];
     __shared__ int sh_rows[CHUNK_DOUBLES / 2];
-    constexpr int DD = D > 0 ? D : 32;
-    const long long j = (long long)blockIdx.x * SET_THREADS + threadIdx.x;
-    const bool live = j < N;
-    double x[DD];
-    if (D > 0) {
+    constexpr int DP = (D + 1) & ~1;
+    const int per = m * DP;
+    const long long ntiles = (N + 2 * SET_THREADS - 1) / (2 * SET_THREADS);
+    const bool single_chunk = P <= polys_per_chunk;     // stage once, then stream tiles of points
+    bool staged = false;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long j0 = tile * (2 * SET_THREADS) + (VEC ? 2 * threadIdx.x : threadIdx.x);
+        const long long j1 = j0 + (VEC ? 1 : SET_THREADS);
+        const bool live0 = j0 < N, live1 = j1 < N;
+        double x0[DP], x1[DP];
 #pragma unroll
-        for (int k = 0; k < DD; ++k) x[k] = live ? __ldg(pts + (size_t)k * N + j) : 0.0;
-    } else {
-        for (int k = 0; k < d; ++k) x[k] = live ? __ldg(pts + (size_t)k * N + j) : 0.0;
-    }
-    bool any = false;
-    const int per = m * (d + 1);
-    for (int p0 = 0; p0 < P; p0 += polys_per_chunk) {
-        const int np = min(polys_per_chunk, P - p0);
-        __syncthreads();
-        // stage [np][m][d] rows then [np][m] right-hand sides
-        for (int e = threadIdx.x; e < np * m * d; e += SET_THREADS) sh[e] = __ldg(A + (size_t)p0 * m * d + e);
-        for (int e = threadIdx.x; e < np * m; e += SET_THREADS) sh[np * m * d + e] = __ldg(b + (size_t)p0 * m + e);
-        for (int e = threadIdx.x; e < np; e += SET_THREADS) sh_rows[e] = m_rows ? min(max(m_rows[p0 + e], 0), m) : m;
-        __syncthreads();
-        (void)per;
-        for (int q = 0; q < np; ++q) {
-            if (mode == 1 && any) break;
-            const bool in = inside_rows<D>(sh + (size_t)q * m * d, sh + (size_t)np * m * d + q * m, sh_rows[q], d, x, abs_tol);
-            if (mode == 0) {
-                if (live) out[(size_t)(p0 + q) * N + j] = in ? 1 : 0;
+        for (int k = 0; k < DP; ++k) {
+            if (VEC) {
+                // N even and j0 even: (j0, j0 + 1) are both live or both dead, 16-byte aligned
+                const double2 v = (k < D && live0) ? __ldcs(reinterpret_cast<const double2*>(pts + (size_t)k * N + j0))
+                                                   : make_double2(0.0, 0.0);
+                x0[k] = v.x;
+                x1[k] = v.y;
             } else {
-                any = any || in;
+                x0[k] = (k < D && live0) ? __ldcs(pts + (size_t)k * N + j0) : 0.0;
+                x1[k] = (k < D && live1) ? __ldcs(pts + (size_t)k * N + j1) : 0.0;
+            }
+        }
+        bool any0 = false, any1 = false;
+        for (int p0 = 0; p0 < P; p0 += polys_per_chunk) {
+            const int np = min(polys_per_chunk, P - p0);
+            if (!(single_chunk && staged)) {
+                __syncthreads();
+                // stage [np][m][DP] rows (pad column zero) then [np][m] right-hand sides
+                for (int e = threadIdx.x; e < np * per; e += SET_THREADS) {
+                    const int row = e / DP, k = e - row * DP;
+                    sh[e] = k < D ? __ldg(A + ((size_t)p0 * m + row) * D + k) : 0.0;
+                }
+                for (int e = threadIdx.x; e < np * m; e += SET_THREADS) sh[np * per + e] = __ldg(b + (size_t)p0 * m + e);
+                for (int e = threadIdx.x; e < np; e += SET_THREADS) sh_rows[e] = m_rows ? min(max(m_rows[p0 + e], 0), m) : m;
+                __syncthreads();
+                staged = true;
+            }
+            for (int q = 0; q < np; ++q) {
+                if (mode == 1 && any0 && any1) break;
+                bool in0, in1;
+                inside_rows_x2<DP>(sh + (size_t)q * per, sh + (size_t)np * per + q * m, sh_rows[q], x0, x1, abs_tol, in0, in1);
+                if (mode == 0) {
+                    uint8_t* o = out + (size_t)(p0 + q) * N;
+                    if (VEC) {
+                        if (live0) __stcs(reinterpret_cast<uchar2*>(o + j0), make_uchar2(in0 ? 1 : 0, in1 ? 1 : 0));
+                    } else {
+                        if (live0) o[j0] = in0 ? 1 : 0;
+                        if (live1) o[j1] = in1 ? 1 : 0;
+                    }
+                } else {
+                    any0 = any0 || in0;
+                    any1 = any1 || in1;
+                }
+            }
+        }
+        if (mode == 1) {
+            if (VEC) {
+                if (live0) __stcs(reinterpret_cast<uchar2*>(out + j0), make_uchar2(any0 ? 1 : 0, any1 ? 1 : 0));
+            } else {
+                if (live0) out[j0] = any0 ? 1 : 0;
+                if (live1) out[j1] = any1 ? 1 : 0;
             }
         }
     }
-    if (mode == 1 && live) out[j] = any ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------
 // volume: count[p] += #{ j < N : A (l + u_j * (hi - lo)) - b < 0 }, with
 // u = default_rng(seed).random((d, N)) regenerated from the PCG64 state
 // (polytope.py:1583-1591).  grid = (P, S): S CTAs share the samples of one
-// polytope, thread t of split s takes samples j = s*T + t, then + S*T, ...
+// polytope; every thread owns a contiguous run of samples, so after one
+// O(log) jump per thread each draw is a single 128-bit multiply-add.
 // ------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(SET_THREADS) volume_kernel(const double* __restrict__ A, const double* __restrict__ b,
@@ -136,59 +206,66 @@ __global__ void __launch_bounds__(SET_THREADS) volume_kernel(const double* __res
                                                              const double* __restrict__ lo, const double* __restrict__ hi,
                                                              long long N, const uint64_t* __restrict__ rng,
                                                              unsigned long long* __restrict__ count) {
-    extern __shared__ double sh[];       // [m][d] rows | [m] b
-    constexpr int DD = D > 0 ? D : 32;
+    extern __shared__ __align__(16) double sh[];       // [m][DP] rows | [m] b
+    constexpr int DP = (D + 1) & ~1;
     __shared__ unsigned long long sh_cnt;
-    __shared__ u128 sh_coef[4];          // jump by N: (mult, plus); jump by stride-1: (mult, plus)
+    __shared__ u128 sh_coef[2];          // jump by N: (mult, plus)
     const int p = blockIdx.x;
     const int mm = m_rows ? min(max(m_rows[p], 0), m) : m;
-    for (int e = threadIdx.x; e < m * d; e += SET_THREADS) sh[e] = __ldg(A + (size_t)p * m * d + e);
-    for (int e = threadIdx.x; e < m; e += SET_THREADS) sh[m * d + e] = __ldg(b + (size_t)p * m + e);
+    for (int e = threadIdx.x; e < m * DP; e += SET_THREADS) {
+        const int row = e / DP, k = e - row * DP;
+        sh[e] = k < D ? __ldg(A + ((size_t)p * m + row) * D + k) : 0.0;
+    }
+    for (int e = threadIdx.x; e < m; e += SET_THREADS) sh[m * DP + e] = __ldg(b + (size_t)p * m + e);
     Pcg g;
     g.state = ((u128)rng[4 * p + 0] << 64) | rng[4 * p + 1];
     g.inc = ((u128)rng[4 * p + 2] << 64) | rng[4 * p + 3];
-    const long long stride = (long long)gridDim.y * SET_THREADS;
     if (threadIdx.x == 0) {
         sh_cnt = 0;
         pcg_jump_coeffs(g.inc, (unsigned long long)N, sh_coef[0], sh_coef[1]);
-        pcg_jump_coeffs(g.inc, (unsigned long long)(stride - 1), sh_coef[2], sh_coef[3]);
     }
     __syncthreads();
-    const long long j0 = (long long)blockIdx.y * SET_THREADS + threadIdx.x;
-    double l[DD], w[DD];
-    u128 st[DD];
+    // samples [j_begin, j_end) of this thread
+    const long long nthreads = (long long)gridDim.y * SET_THREADS;
+    const long long per_thread = (N + nthreads - 1) / nthreads;
+    const long long j_begin = ((long long)blockIdx.y * SET_THREADS + threadIdx.x) * per_thread;
+    const long long j_end = j_begin + per_thread < N ? j_begin + per_thread : N;
+    double l[DP], w[DP];
+    u128 st[DP];
     {
         // stream position of coordinate k for sample j is k*N + j
         u128 am, ap;
-        pcg_jump_coeffs(g.inc, (unsigned long long)j0, am, ap);
+        pcg_jump_coeffs(g.inc, (unsigned long long)(j_begin < N ? j_begin : 0), am, ap);
         u128 s = g.state * am + ap;
-        const int dd = D > 0 ? DD : d;
 #pragma unroll
-        for (int k = 0; k < DD; ++k) {
-            if (k < dd) {
-                st[k] = s;
-                s = s * sh_coef[0] + sh_coef[1];
-                l[k] = lo[(size_t)p * d + k];
-                w[k] = __dsub_rn(hi[(size_t)p * d + k], l[k]);
-            }
+        for (int k = 0; k < DP; ++k) {
+            st[k] = s;
+            s = s * sh_coef[0] + sh_coef[1];
+            l[k] = k < D ? lo[(size_t)p * d + k] : 0.0;
+            w[k] = k < D ? __dsub_rn(hi[(size_t)p * d + k], l[k]) : 0.0;
         }
     }
-    unsigned long long mine = 0;
-    for (long long j = j0; j < N; j += stride) {
-        double x[DD];
-        const int dd = D > 0 ? DD : d;
+    unsigned mine = 0;
+    for (long long j = j_begin; j < j_end; j += 2) {
+        double x0[DP], x1[DP];
 #pragma unroll
-        for (int k = 0; k < DD; ++k) {
-            if (k < dd) {
-                const double u = pcg_next_double(st[k], g.inc);
-                x[k] = __dadd_rn(l[k], __dmul_rn(u, w[k]));
-                st[k] = st[k] * sh_coef[2] + sh_coef[3];     // skip the draws of the other threads
+        for (int k = 0; k < DP; ++k) {
+            if (k < D) {
+                const double u0 = pcg_next_double(st[k], g.inc);
+                const double u1 = pcg_next_double(st[k], g.inc);
+                x0[k] = __dadd_rn(l[k], __dmul_rn(u0, w[k]));
+                x1[k] = __dadd_rn(l[k], __dmul_rn(u1, w[k]));
+            } else {
+                x0[k] = 0.0;
+                x1[k] = 0.0;
             }
         }
-        mine += inside_rows<D>(sh, sh + m * d, mm, d, x, 0.0) ? 1ull : 0ull;
+        bool in0, in1;
+        inside_rows_x2<DP>(sh, sh + m * DP, mm, x0, x1, 0.0, in0, in1);
+        mine += (in0 ? 1u : 0u) + ((in1 && j + 1 < j_end) ? 1u : 0u);
     }
-    mine = __reduce_add_sync(0xffffffffu, (unsigned)mine);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sh_cnt, mine);
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&sh_cnt, (unsigned long long)mine);
     __syncthreads();
     if (threadIdx.x == 0 && sh_cnt) atomicAdd(count + p, sh_cnt);
 }
@@ -255,9 +332,17 @@ __global__ void __launch_bounds__(SET_THREADS) sweep_kernel(const double* __rest
 template <int D>
 static int launch_contains(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, const double* pts,
                            long long N, double abs_tol, int mode, uint8_t* out, cudaStream_t st) {
-    const int per = m * (d + 1);
+    const int per = m * (((D + 1) & ~1) + 1);
     const int ppc = CHUNK_DOUBLES / per;
-    contains_kernel<D><<<blocks_for(N, SET_THREADS), SET_THREADS, 0, st>>>(A, b, m_rows, P, m, d, pts, N, abs_tol, mode, out, ppc);
+    // persistent-ish grid: a whole number of waves, every CTA streams several 512-point tiles
+    const int sms = sm_count();
+    if (!sms) return PB200_ECUDA;
+    long long grid = (long long)sms * 5 * 4;
+    const long long ntiles = (N + 2 * SET_THREADS - 1) / (2 * SET_THREADS);
+    if (ntiles < grid) grid = ntiles;
+    const bool vec = (N % 2 == 0) && ((uintptr_t)pts % 16 == 0) && ((uintptr_t)out % 2 == 0);
+    if (vec) contains_kernel<D, true><<<(unsigned)grid, SET_THREADS, 0, st>>>(A, b, m_rows, P, m, d, pts, N, abs_tol, mode, out, ppc);
+    else contains_kernel<D, false><<<(unsigned)grid, SET_THREADS, 0, st>>>(A, b, m_rows, P, m, d, pts, N, abs_tol, mode, out, ppc);
     count_launch();
     PB_CHECK_CUDA(cudaGetLastError());
     return PB200_OK;
@@ -273,7 +358,7 @@ static int launch_volume(const double* A, const double* b, const int32_t* m_rows
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
-    const size_t smem = sizeof(double) * (size_t)m * (d + 1);
+    const size_t smem = sizeof(double) * (size_t)m * (((D + 1) & ~1) + 1);
     PB_CHECK_CUDA(cudaFuncSetAttribute(volume_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     volume_kernel<D><<<dim3((unsigned)P, (unsigned)splits), SET_THREADS, smem, st>>>(A, b, m_rows, m, d, lo, hi, N, rng, count);
     count_launch();
@@ -283,23 +368,38 @@ static int launch_volume(const double* A, const double* b, const int32_t* m_rows
 
 #define PB_DISPATCH_D(d, FN, ...)                                  \
     switch (d) {                                                   \
-        case 1: return FN<1>(__VA_ARGS__);                         \
-        case 2: return FN<2>(__VA_ARGS__);                         \
-        case 3: return FN<3>(__VA_ARGS__);                         \
-        case 4: return FN<4>(__VA_ARGS__);                         \
-        case 5: return FN<5>(__VA_ARGS__);                         \
-        case 6: return FN<6>(__VA_ARGS__);                         \
-        case 7: return FN<7>(__VA_ARGS__);                         \
-        case 8: return FN<8>(__VA_ARGS__);                         \
-        case 9: return FN<9>(__VA_ARGS__);                         \
-        case 10: return FN<10>(__VA_ARGS__);                       \
-        case 11: return FN<11>(__VA_ARGS__);                       \
-        case 12: return FN<12>(__VA_ARGS__);                       \
-        case 13: return FN<13>(__VA_ARGS__);                       \
-        case 14: return FN<14>(__VA_ARGS__);                       \
-        case 15: return FN<15>(__VA_ARGS__);                       \
-        case 16: return FN<16>(__VA_ARGS__);                       \
-        default: return FN<0>(__VA_ARGS__);                        \
+        case 1: return FN<1>(__VA_ARGS__);                      \
+        case 2: return FN<2>(__VA_ARGS__);                      \
+        case 3: return FN<3>(__VA_ARGS__);                      \
+        case 4: return FN<4>(__VA_ARGS__);                      \
+        case 5: return FN<5>(__VA_ARGS__);                      \
+        case 6: return FN<6>(__VA_ARGS__);                      \
+        case 7: return FN<7>(__VA_ARGS__);                      \
+        case 8: return FN<8>(__VA_ARGS__);                      \
+        case 9: return FN<9>(__VA_ARGS__);                      \
+        case 10: return FN<10>(__VA_ARGS__);                      \
+        case 11: return FN<11>(__VA_ARGS__);                      \
+        case 12: return FN<12>(__VA_ARGS__);                      \
+        case 13: return FN<13>(__VA_ARGS__);                      \
+        case 14: return FN<14>(__VA_ARGS__);                      \
+        case 15: return FN<15>(__VA_ARGS__);                      \
+        case 16: return FN<16>(__VA_ARGS__);                      \
+        case 17: return FN<17>(__VA_ARGS__);                      \
+        case 18: return FN<18>(__VA_ARGS__);                      \
+        case 19: return FN<19>(__VA_ARGS__);                      \
+        case 20: return FN<20>(__VA_ARGS__);                      \
+        case 21: return FN<21>(__VA_ARGS__);                      \
+        case 22: return FN<22>(__VA_ARGS__);                      \
+        case 23: return FN<23>(__VA_ARGS__);                      \
+        case 24: return FN<24>(__VA_ARGS__);                      \
+        case 25: return FN<25>(__VA_ARGS__);                      \
+        case 26: return FN<26>(__VA_ARGS__);                      \
+        case 27: return FN<27>(__VA_ARGS__);                      \
+        case 28: return FN<28>(__VA_ARGS__);                      \
+        case 29: return FN<29>(__VA_ARGS__);                      \
+        case 30: return FN<30>(__VA_ARGS__);                      \
+        case 31: return FN<31>(__VA_ARGS__);                      \
+        default: return FN<32>(__VA_ARGS__);                       \
     }
 
 }  // namespace pb200
@@ -312,7 +412,7 @@ int pb200_contains_batch(const double* A, const double* b, const int32_t* m_rows
                          long long N, double abs_tol, int any_of, uint8_t* out, void* stream) {
     if (P < 0 || N < 0 || !A || !b || !points || !out) return fail(PB200_EINVAL, "pb200_contains_batch: null pointer or negative size");
     if (d < 1 || d > 32) return fail(PB200_EUNSUPPORTED, "contains: need 1 <= d <= 32");
-    if (m < 1 || m * (d + 1) > CHUNK_DOUBLES) return fail(PB200_EUNSUPPORTED, "contains: need 1 <= m and m*(d+1) <= 4096");
+    if (m < 1 || m * (d + 3) > CHUNK_DOUBLES) return fail(PB200_EUNSUPPORTED, "contains: need 1 <= m and m*(d+3) <= 4096");
     if (N == 0) return PB200_OK;
     if (P == 0) {
         if (any_of) PB_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)N, (cudaStream_t)stream));

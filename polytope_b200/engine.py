@@ -311,7 +311,10 @@ def _default_facet_cap(nmax, d):
         return nmax + 16
     if d == 3:
         return 4 * nmax + 64
-    return int(min(max(2048, 16 * nmax * d), 1 << 16))
+    # facets grow like nmax^floor(d/2): start generous (the workspace is (20 d + 24) bytes per
+    # slot and CTA), hull_batch retries with 4x on HULL_FACET_CAP
+    base = 4096 if d <= 6 else 16384 if d <= 9 else 65536
+    return int(max(base, 8 * nmax))
 
 
 def hull_batch(points, n_pts=None, abs_tol=ABS_TOL, facet_cap=None, out_cap=None, max_tries=6):

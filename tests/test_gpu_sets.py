@@ -96,7 +96,7 @@ def test_contains_matches_reference(golden):
     assert r1.contains(pts, abs_tol=0).tolist() == [False, False, True, False, False]
 
 
-@pytest.mark.parametrize('P,m,d,N', [(1, 6, 3, 100000), (40, 32, 8, 30000), (300, 12, 4, 5000), (7, 64, 16, 2500),
+@pytest.mark.parametrize('P,m,d,N', [(1, 6, 3, 100000), (2, 6, 3, 99999), (5, 9, 7, 1), (40, 32, 8, 30000), (300, 12, 4, 5000), (7, 64, 16, 2500),
                                      (3, 20, 20, 1000)])
 def test_contains_batch_vs_oracle_ragged(P, m, d, N):
     from polytope_b200 import engine
