@@ -172,16 +172,15 @@ __device__ __forceinline__ unsigned s_cholesky(double* Ms, int n, double add_dia
                 L[i * (i + 1) / 2 + j] = fma(-L[i * (i + 1) / 2 + k], L[j * (j + 1) / 2 + k], L[i * (i + 1) / 2 + j]);
     }
     __syncwarp();
-    // lane i writes row i of the symmetric array (all lanes hold identical values)
+    // every lane holds identical values: all of them store the whole symmetric array
+    // (same address, same data -- one wavefront per store, no divergent branches)
 #pragma unroll
     for (int i = 0; i < NS; ++i)
-        if (lane == i) {
 #pragma unroll
-            for (int j = 0; j < NS; j += 2) {
-                const double a = j <= i ? L[i * (i + 1) / 2 + j] : L[j * (j + 1) / 2 + i];
-                const double b = j + 1 <= i ? L[i * (i + 1) / 2 + j + 1] : L[(j + 1) * (j + 2) / 2 + i];
-                *reinterpret_cast<double2*>(Ms + i * NS + j) = make_double2(a, b);
-            }
+        for (int j = 0; j < NS; j += 2) {
+            const double a = j <= i ? L[i * (i + 1) / 2 + j] : L[j * (j + 1) / 2 + i];
+            const double b = j + 1 <= i ? L[i * (i + 1) / 2 + j + 1] : L[(j + 1) * (j + 2) / 2 + i];
+            *reinterpret_cast<double2*>(Ms + i * NS + j) = make_double2(a, b);
         }
     __syncwarp();
     return skipped & ((1u << n) - 1u);
@@ -197,9 +196,10 @@ __device__ __forceinline__ void load_vec(const double* src, double (&v)[NS]) {
 
 // ---- replicated solve of (L L') y = r for the NR right-hand sides stored as
 // consecutive 8-vectors at X; solutions overwrite them.  L is read by broadcast.
-// `nrhs` (warp-uniform, <= NR) right-hand sides are actually solved.
+// All NR systems are always solved (a caller with fewer right-hand sides passes
+// zeros): a run-time count cost one register move per DFMA (profiles/r01e_*).
 template <int NR>
-__device__ __forceinline__ void s_solve(const double* Ms, double* X, int lane, int nrhs = NR) {
+__device__ __forceinline__ void s_solve(const double* Ms, double* X, int lane) {
     double a[NR][NS];
 #pragma unroll
     for (int v = 0; v < NR; ++v) load_vec(X + v * NS, a[v]);
@@ -208,32 +208,29 @@ __device__ __forceinline__ void s_solve(const double* Ms, double* X, int lane, i
         double row[NS];
         load_vec(Ms + k * NS, row);
 #pragma unroll
-        for (int v = 0; v < NR; ++v)
-            if (v < nrhs) {
-                a[v][k] *= row[k];
+        for (int v = 0; v < NR; ++v) {
+            a[v][k] *= row[k];
 #pragma unroll
-                for (int i = k + 1; i < NS; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
-            }
+            for (int i = k + 1; i < NS; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
+        }
     }
 #pragma unroll
     for (int k = NS - 1; k >= 0; --k) {
         double row[NS];
         load_vec(Ms + k * NS, row);
 #pragma unroll
-        for (int v = 0; v < NR; ++v)
-            if (v < nrhs) {
-                a[v][k] *= row[k];
+        for (int v = 0; v < NR; ++v) {
+            a[v][k] *= row[k];
 #pragma unroll
-                for (int i = 0; i < k; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
-            }
+            for (int i = 0; i < k; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
+        }
     }
     __syncwarp();
-    // lanes 0..3 (4..7) write the four 16-byte pieces of solution 0 (1)
+    // identical values in every lane: all lanes store (same address, same data)
 #pragma unroll
     for (int v = 0; v < NR; ++v)
 #pragma unroll
-        for (int j = 0; j < NS; j += 2)
-            if (lane == v * 4 + (j >> 1)) *reinterpret_cast<double2*>(X + v * NS + j) = make_double2(a[v][j], a[v][j + 1]);
+        for (int j = 0; j < NS; j += 2) *reinterpret_cast<double2*>(X + v * NS + j) = make_double2(a[v][j], a[v][j + 1]);
     __syncwarp();
 }
 
@@ -563,7 +560,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                 X2[lane] = rb;
             }
             __syncwarp();
-            s_solve<2>(w.M, X1, lane, (phase == 0 && pass == 0) ? 2 : 1);
+            s_solve<2>(w.M, X1, lane);
             if (phase == 1) {
                 if (own) {
                     if (round < 3) { xp += X1[lane]; Xx[lane] = xp; }
