@@ -19,6 +19,13 @@
 
 namespace pb200 {
 
+// Every branch of the solver is warp-uniform (all lanes hold bitwise identical
+// scalars), but ptxas cannot prove it for conditions computed from butterfly
+// reductions.  Passing such a condition through a vote makes the branch provably
+// uniform, which removes the divergence bookkeeping (BSSY/BSYNC, the
+// WARPSYNC.COLLECTIVE slow path around every shuffle) from the loop body.
+#define PB_UNI(cond) __all_sync(FULL_MASK, (cond))
+
 constexpr int NS = 8;                       // padded column count of this path
 constexpr int NTRI = NS * (NS + 1) / 2;     // packed lower triangle
 
@@ -402,14 +409,14 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                 }
                 slack = warp_min(slack);
                 const bool feasible = slack >= -1e-9 * fmax(1.0, hmax);
-                if (!early) {
+                if (PB_UNI(!early)) {
                     // final polish of a tightly converged iterate: objective must agree
                     const double f1 = warp_sum(cl0 * xp);
-                    if (feasible && (fabs(f1 - f0) <= 1e-6 * fmax(1.0, fabs(f0)))) { res.x = xp; res.fun = f1; }
+                    if (PB_UNI(feasible && (fabs(f1 - f0) <= 1e-6 * fmax(1.0, fabs(f0))))) { res.x = xp; res.fun = f1; }
                     break;
                 }
                 tight = warp_max(tight);
-                if (feasible && tight <= 1e-9 * fmax(1.0, hmax)) {
+                if (PB_UNI(feasible && tight <= 1e-9 * fmax(1.0, hmax))) {
                     // start the dual certificate: y = z / tau on the active rows
                     const double te = 1.0 / tau;
 #pragma unroll
@@ -435,7 +442,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                     const double rdmax = warp_max(rd);
                     ymin = warp_min(ymin);
                     ymax = warp_max(ymax);
-                    if (rdmax <= 1e-9 * sqrt(nc2) && ymin >= -1e-9 * fmax(1.0, ymax)) {
+                    if (PB_UNI(rdmax <= 1e-9 * sqrt(nc2) && ymin >= -1e-9 * fmax(1.0, ymax))) {
                         // primal feasible, dual feasible, complementary: optimal
                         res.status = ST_OPTIMAL;
                         res.x = xp;
@@ -445,7 +452,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                     fallback = true;
                 }
             }
-            if (fallback) {
+            if (PB_UNI(fallback)) {
                 // resume the interior-point iterations from the untouched iterate
                 phase = 0; early = false;
                 if (own) Xx[lane] = xl;
@@ -472,7 +479,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             const double gap = sz * t2;
             // relgap <= tol  <=>  gap <= tol * (-pcost)  or  gap <= tol * dcost
             const double gapref = pcost < 0.0 ? -pcost : (dcost > 0.0 ? dcost : 0.0);
-            if (!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300)) { res.status = ST_NUMERICAL; break; }
+            if (PB_UNI(!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300))) { res.status = ST_NUMERICAL; break; }
             const bool converged = rz2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nh2 && rx2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nc2 &&
                                    (gap <= LP_GAP_TOL || gap <= LP_GAP_TOL * gapref);
             // At the loose tolerance the active set is usually already identified:
@@ -482,8 +489,8 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             const bool loosely = !tried && !lineal &&
                                  rz2 * t2 <= LP_EARLY_TOL * LP_EARLY_TOL * nh2 && rx2 * t2 <= LP_EARLY_TOL * LP_EARLY_TOL * nc2 &&
                                  (gap <= LP_EARLY_TOL || gap <= LP_EARLY_TOL * gapref);
-            if (converged || loosely) {
-                if (converged && lineal) { res.status = ST_UNBOUNDED; break; }
+            if (PB_UNI(converged || loosely)) {
+                if (PB_UNI(converged && lineal)) { res.status = ST_UNBOUNDED; break; }
                 early = !converged;
                 tried = true;
                 // ---- extract, then polish on the active set (see lp_warp.cuh) ----
@@ -496,7 +503,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                     nact += act[r] ? 1 : 0;
                 }
                 nact = __reduce_add_sync(FULL_MASK, nact);
-                if (converged) {
+                if (PB_UNI(converged)) {
                     f0 = warp_sum(cl0 * xp);
                     res.status = ST_OPTIMAL; res.x = xp; res.fun = f0;
                     if (nact == 0) break;
@@ -511,12 +518,12 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                 }
                 early = false;      // nothing active yet: keep iterating
             }
-            if (tau < 1e-3 * kap) {
-                if (hz < 0.0) {
+            if (PB_UNI(tau < 1e-3 * kap)) {
+                if (PB_UNI(hz < 0.0)) {
                     const double gz2 = warp_sum(gzl * gzl);
-                    if (sqrt(gz2 * nh2 / nc2) <= 10.0 * LP_FEAS_TOL * (-hz)) { res.status = ST_INFEASIBLE; break; }
+                    if (PB_UNI(sqrt(gz2 * nh2 / nc2) <= 10.0 * LP_FEAS_TOL * (-hz))) { res.status = ST_INFEASIBLE; break; }
                 }
-                if (cx < 0.0 && sqrt(gxs2 * nc2 / nh2) <= 10.0 * LP_FEAS_TOL * (-cx)) { res.status = ST_UNBOUNDED; break; }
+                if (PB_UNI(cx < 0.0 && sqrt(gxs2 * nc2 / nh2) <= 10.0 * LP_FEAS_TOL * (-cx))) { res.status = ST_UNBOUNDED; break; }
             }
             if (it == LP_MAX_ITER) break;
         }
@@ -531,10 +538,10 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                 __syncwarp();
             }
             const unsigned skipped = s_cholesky(w.M, n, add_diag, lane);
-            if (phase == 0 && it == 0 && skipped && !lineal) {
+            if (PB_UNI(phase == 0 && it == 0 && skipped && !lineal)) {
                 // rank-deficient G: if c has a component in null(G) the LP is unbounded
                 // whenever it is feasible -> continue with c = 0 and report 3 instead of 0
-                if (s_objective_leaves_range<RPL>(w, mk, cl, lane)) {
+                if (PB_UNI(s_objective_leaves_range<RPL>(w, mk, cl, lane))) {
                     lineal = true;
                     cl = 0.0;
                     if (own) Xc[lane] = 0.0;

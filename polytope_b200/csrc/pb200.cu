@@ -324,7 +324,9 @@ __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long
 template <int RPL, class Prob>
 __global__ void __launch_bounds__(WPC * 32, PB200_SMALL_MINB) lp_kernel_small(const Prob prob, long long n_items) {
     extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // warp index through a warp reduction: the result is provably warp-uniform, so the
+    // item loop below (and everything it controls) is uniform control flow for ptxas
+    const int lane = threadIdx.x & 31, wib = __reduce_max_sync(FULL_MASK, threadIdx.x >> 5);
     const int n = prob.n();
     const SmallScratch w = lps_carve(smem + (size_t)wib * lps_scratch_doubles(RPL), RPL);
     const long long nwarps = (long long)gridDim.x * WPC;
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(WPC * 32, PB200_SMALL_MINB) lp_kernel_small(co
         int m;
         double cl;
         double h[RPL];
-        if (!prob.template load<RPL>(t, w, lane, m, cl, h, cached)) continue;
+        if (PB_UNI(!prob.template load<RPL>(t, w, lane, m, cl, h, cached))) continue;
         const SmallResult sr = lp_solve_small<RPL>(w, m, n, cl, h);
         LpResult res;
         res.status = sr.status; res.iters = sr.iters; res.fun = sr.fun; res.x = sr.x;
