@@ -165,7 +165,7 @@ template <int RPL, bool SMALL>
 __global__ void __launch_bounds__(DIFF_WPC * 32) diff_kernel(const DiffArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ DiffState states[DIFF_WPC];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = __reduce_max_sync(FULL_MASK, threadIdx.x >> 5);   // provably uniform
     const int d = a.d, n = d + 1;
     typedef Solver<RPL, SMALL> S;
     const typename S::Scratch w = S::carve(smem + (size_t)wib * S::doubles(n), n);

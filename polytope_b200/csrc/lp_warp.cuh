@@ -33,6 +33,12 @@
 namespace pb200 {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
+// Every branch of the solvers is warp-uniform (all lanes hold bitwise identical
+// scalars), but ptxas cannot prove it for conditions computed from butterfly
+// reductions.  Passing such a condition through a vote makes the branch provably
+// uniform, which removes the divergence bookkeeping (BSSY/BSYNC, the
+// WARPSYNC.COLLECTIVE slow path around every shuffle) from the loop body.
+#define PB_UNI(cond) __all_sync(FULL_MASK, (cond))
 constexpr int LP_MAX_ITER = 60;
 constexpr int LP_MAX_N = 32;            // columns (n-vectors are lane-owned)
 constexpr double LP_FEAS_TOL = 1e-9;
@@ -317,25 +323,25 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
         double relgap = 1e300;
         if (pcost < 0.0) relgap = gap / -pcost;
         else if (dcost > 0.0) relgap = gap / dcost;
-        if (!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300)) { res.status = ST_NUMERICAL; break; }
-        if (pres <= LP_FEAS_TOL && dres <= LP_FEAS_TOL && (gap <= LP_GAP_TOL || relgap <= LP_GAP_TOL)) {
+        if (PB_UNI(!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300))) { res.status = ST_NUMERICAL; break; }
+        if (PB_UNI(pres <= LP_FEAS_TOL && dres <= LP_FEAS_TOL && (gap <= LP_GAP_TOL || relgap <= LP_GAP_TOL))) {
             res.status = ST_OPTIMAL; break;
         }
-        if (tau < 1e-3 * kap) {
-            if (hz < 0.0) {
+        if (PB_UNI(tau < 1e-3 * kap)) {
+            if (PB_UNI(hz < 0.0)) {
                 const double gz2 = warp_sum(gz * gz);
-                if (sqrt(gz2) / (-hz) * nh / nc <= 10.0 * LP_FEAS_TOL) { res.status = ST_INFEASIBLE; break; }
+                if (PB_UNI(sqrt(gz2) / (-hz) * nh / nc <= 10.0 * LP_FEAS_TOL)) { res.status = ST_INFEASIBLE; break; }
             }
-            if (cx < 0.0) {
+            if (PB_UNI(cx < 0.0)) {
                 gxs2 = warp_sum(gxs2);
-                if (sqrt(gxs2) / (-cx) * nc / nh <= 10.0 * LP_FEAS_TOL) { res.status = ST_UNBOUNDED; break; }
+                if (PB_UNI(sqrt(gxs2) / (-cx) * nc / nh <= 10.0 * LP_FEAS_TOL)) { res.status = ST_UNBOUNDED; break; }
             }
         }
         if (it == LP_MAX_ITER) break;
         // ---- factor M = G' D G ----
         form_normal_matrix(w, mk, n, lane);
         const unsigned skipped = cholesky(w, n, lane);
-        if (it == 0 && skipped) {
+        if (PB_UNI(it == 0 && skipped)) {
             // G is column-rank deficient.  If c has a component in null(G) the LP
             // is unbounded whenever it is feasible: continue with the feasibility
             // problem (c = 0) and report 3 instead of 0.
@@ -351,7 +357,7 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
             gt_times_slots(w, mk, n, 1, lane);
             const double rc = own ? c - w.R[lane] : 0.0;
             const double rmax = warp_max(fabs(rc)), cmax = warp_max(fabs(c));
-            if (rmax > 1e-9 * fmax(cmax, 1e-300)) {
+            if (PB_UNI(rmax > 1e-9 * fmax(cmax, 1e-300))) {
                 lineal = true;
                 c = 0.0;
                 nc = 1.0;
@@ -443,7 +449,7 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
             if (live[r]) { s[r] = fma(alpha, ds[r], s[r]); z[r] = fma(alpha, dz[r], z[r]); }
     }
     if (lineal && res.status == ST_OPTIMAL) res.status = ST_UNBOUNDED;
-    if (res.status != ST_OPTIMAL) return res;
+    if (PB_UNI(res.status != ST_OPTIMAL)) return res;
 
     // ---- extract and polish ----
     const double tinv = 1.0 / tau;
@@ -461,7 +467,7 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
     __syncwarp();
     res.x = xs;
     res.fun = f0;
-    if (nact == 0) return res;
+    if (PB_UNI(nact == 0)) return res;
     form_normal_matrix(w, mk, n, lane);
     {
         const double dg = own ? w.M[lane * w.LDM + lane] : 0.0;

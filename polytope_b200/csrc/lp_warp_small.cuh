@@ -19,13 +19,6 @@
 
 namespace pb200 {
 
-// Every branch of the solver is warp-uniform (all lanes hold bitwise identical
-// scalars), but ptxas cannot prove it for conditions computed from butterfly
-// reductions.  Passing such a condition through a vote makes the branch provably
-// uniform, which removes the divergence bookkeeping (BSSY/BSYNC, the
-// WARPSYNC.COLLECTIVE slow path around every shuffle) from the loop body.
-#define PB_UNI(cond) __all_sync(FULL_MASK, (cond))
-
 constexpr int NS = 8;                       // padded column count of this path
 constexpr int NTRI = NS * (NS + 1) / 2;     // packed lower triangle
 

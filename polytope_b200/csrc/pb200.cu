@@ -296,7 +296,7 @@ struct AdjacentLP {
 template <int RPL, class Prob>
 __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long n_items) {
     extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = __reduce_max_sync(FULL_MASK, threadIdx.x >> 5);   // provably uniform
     const int n = prob.n();
     const WarpScratch w = lp_carve(smem + (size_t)wib * lp_scratch_doubles(RPL, n), RPL, n);
     // each warp owns a contiguous range of items, so consecutive LPs of one
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long
         int m;
         double c;
         double h[RPL];
-        if (!prob.template load<RPL>(t, w, lane, m, c, h, cached)) continue;
+        if (PB_UNI(!prob.template load<RPL>(t, w, lane, m, c, h, cached))) continue;
         const LpResult res = lp_solve_warp<RPL>(w, m, n, c, h);
         prob.template store<RPL>(t, lane, res);
         __syncwarp();
