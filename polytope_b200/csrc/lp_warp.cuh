@@ -243,6 +243,107 @@ struct LpResult {
     double fun;    // c'x, valid if status == 0
 };
 
+// Active-set polish of an interior-point iterate, optionally with an optimality
+// certificate.  Rows with z > s are taken as the optimal face; x is moved by the
+// minimum-norm correction onto their affine hull (3 regularised normal-equation
+// rounds).  certify == false (tightly converged iterate): accept if no row is
+// violated and the objective agrees with the iterate's.  certify == true (loosely
+// converged iterate): accept only if additionally the active rows are tight and
+// the least-squares-refined multipliers y (two rounds of y -= G_B (G_B'G_B)^-1
+// (G_B'y + c)) are dual feasible: y >= 0, G_B'y + c = 0 -- i.e. (xp, y) is a
+// complementary primal-dual optimal pair.  Overwrites w.M, w.d, w.V, w.u, w.R.
+template <int RPL>
+__device__ __forceinline__ bool polish_active_set(const WarpScratch& w, int mk, int n, int lane, bool own, double c_orig, double nc,
+                                                  double hmax, const double (&h)[RPL], const bool (&live)[RPL],
+                                                  const double (&s)[RPL], const double (&z)[RPL], double tau, double xs,
+                                                  bool certify, double& xp_out, double& fp_out) {
+    const int NP = w.NP;
+    bool act[RPL];
+    int nact = 0;
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        act[r] = live[r] && (z[r] > s[r]);
+        nact += act[r] ? 1 : 0;
+        w.d[lane + 32 * r] = act[r] ? 1.0 : 0.0;
+    }
+    nact = __reduce_add_sync(FULL_MASK, nact);
+    __syncwarp();
+    if (PB_UNI(nact == 0)) return false;
+    const double f0 = warp_sum(c_orig * xs);
+    form_normal_matrix(w, mk, n, lane);
+    {
+        const double dg = own ? w.M[lane * w.LDM + lane] : 0.0;
+        const double reg = 1e-9 * fmax(1.0, warp_max(dg));
+        if (own) w.M[lane * w.LDM + lane] = dg + reg;
+        __syncwarp();
+    }
+    cholesky(w, n, lane);
+    double xp = xs;
+    double gxp[1][RPL];
+    double y[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) y[r] = 0.0;
+    const double te = 1.0 / tau;
+    bool ok = true;
+    // rounds 0-2: projection; round 3: checks (+ start of the certificate); 4, 5: refinement
+#pragma unroll 1
+    for (int round = 0; round < 6; ++round) {
+        if (round <= 3) {
+            if (lane < NP) w.u[lane] = own ? xp : 0.0;
+        }
+        __syncwarp();
+        rows_times<RPL, 1>(w, n, 0, lane, gxp);
+        if (round < 3) {
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = act[r] ? h[r] - gxp[0][r] : 0.0;
+        } else if (round == 3) {
+            double slack = 1e300, tight = 0.0;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                if (live[r]) slack = fmin(slack, h[r] - gxp[0][r]);
+                if (act[r]) tight = fmax(tight, fabs(h[r] - gxp[0][r]));
+            }
+            slack = warp_min(slack);
+            const bool feasible = slack >= -1e-9 * fmax(1.0, hmax);
+            const double f1 = warp_sum(c_orig * xp);
+            xp_out = xp;
+            fp_out = f1;
+            if (PB_UNI(!certify)) return feasible && (fabs(f1 - f0) <= 1e-6 * fmax(1.0, fabs(f0)));
+            tight = warp_max(tight);
+            if (PB_UNI(!(feasible && tight <= 1e-9 * fmax(1.0, hmax)))) return false;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                y[r] = act[r] ? z[r] * te : 0.0;
+                w.V[lane + 32 * r] = y[r];
+            }
+        } else {
+            double ymin = 1e300, ymax = 0.0;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) {
+                if (act[r]) { y[r] -= gxp[0][r]; ymin = fmin(ymin, y[r]); ymax = fmax(ymax, y[r]); }
+                w.V[lane + 32 * r] = y[r];
+            }
+            if (round == 5) {
+                __syncwarp();
+                gt_times_slots(w, mk, n, 1, lane);
+                const double rd = own ? fabs(w.R[lane] + c_orig) : 0.0;      // |G_B'y + c|
+                const double rdmax = warp_max(rd);
+                ymin = warp_min(ymin);
+                ymax = warp_max(ymax);
+                ok = rdmax <= 1e-9 * nc && ymin >= -1e-9 * fmax(1.0, ymax);
+                break;
+            }
+        }
+        __syncwarp();
+        gt_times_slots(w, mk, n, 1, lane);
+        double rhs[1] = {own ? (round < 3 ? w.R[lane] : w.R[lane] + c_orig) : 0.0};
+        chol_solve<1>(w, n, lane, rhs);
+        if (round < 3) xp += rhs[0];
+        else if (lane < NP) w.u[lane] = own ? rhs[0] : 0.0;       // next round multiplies G by u
+    }
+    return ok;
+}
+
 // Solve the LP whose G is staged in w.G (rows >= m zero).  `c` is the lane-owned
 // objective component (0 for lanes >= n); h[r] the right-hand side of row
 // lane+32r (ignored for rows >= m; +inf means "no constraint").
@@ -274,10 +375,11 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
     hmax = warp_max(hmax);
     double nc = fmax(1.0, sqrt(warp_sum(c * c)));
     double x = 0.0, tau = 1.0, kap = 1.0;
-    bool lineal = false;
+    bool lineal = false, tried = false;
     LpResult res;
     res.status = ST_ITER_LIMIT; res.iters = 0; res.x = 0.0; res.fun = 0.0;
 
+#pragma unroll 1
     for (int it = 0; it <= LP_MAX_ITER; ++it) {
         res.iters = it;
         // ---- residuals ----
@@ -324,8 +426,30 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
         if (pcost < 0.0) relgap = gap / -pcost;
         else if (dcost > 0.0) relgap = gap / dcost;
         if (PB_UNI(!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300))) { res.status = ST_NUMERICAL; break; }
-        if (PB_UNI(pres <= LP_FEAS_TOL && dres <= LP_FEAS_TOL && (gap <= LP_GAP_TOL || relgap <= LP_GAP_TOL))) {
-            res.status = ST_OPTIMAL; break;
+        const bool converged = pres <= LP_FEAS_TOL && dres <= LP_FEAS_TOL && (gap <= LP_GAP_TOL || relgap <= LP_GAP_TOL);
+        // At the loose tolerance the active set is usually already identified: try the
+        // polish there and accept it only with a full optimality certificate (primal
+        // feasible, active rows tight, y >= 0 with G_B'y + c = 0); otherwise keep
+        // iterating to the tight tolerance (same scheme as lp_warp_small.cuh).
+        const bool loosely = !tried && !lineal && pres <= LP_EARLY_TOL && dres <= LP_EARLY_TOL &&
+                             (gap <= LP_EARLY_TOL || relgap <= LP_EARLY_TOL);
+        if (PB_UNI(converged || loosely)) {
+            if (PB_UNI(converged && lineal)) { res.status = ST_UNBOUNDED; break; }
+            tried = true;
+            double xp, fp;
+            const double xs = x / tau;
+            const bool ok = polish_active_set<RPL>(w, mk, n, lane, own, c_orig, nc, hmax, h, live, s, z, tau, xs, !converged, xp, fp);
+            if (PB_UNI(converged)) {
+                res.status = ST_OPTIMAL;
+                res.x = ok ? xp : xs;
+                res.fun = ok ? fp : warp_sum(c_orig * xs);
+                break;
+            }
+            if (PB_UNI(ok)) { res.status = ST_OPTIMAL; res.x = xp; res.fun = fp; break; }
+            // not certified: restore the row weights the polish overwrote and go on
+#pragma unroll
+            for (int r = 0; r < RPL; ++r) w.d[lane + 32 * r] = d[r];
+            __syncwarp();
         }
         if (PB_UNI(tau < 1e-3 * kap)) {
             if (PB_UNI(hz < 0.0)) {
@@ -448,57 +572,6 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
         for (int r = 0; r < RPL; ++r)
             if (live[r]) { s[r] = fma(alpha, ds[r], s[r]); z[r] = fma(alpha, dz[r], z[r]); }
     }
-    if (lineal && res.status == ST_OPTIMAL) res.status = ST_UNBOUNDED;
-    if (PB_UNI(res.status != ST_OPTIMAL)) return res;
-
-    // ---- extract and polish ----
-    const double tinv = 1.0 / tau;
-    double xs = x * tinv;
-    const double f0 = warp_sum(c_orig * xs);
-    bool act[RPL];
-    int nact = 0;
-#pragma unroll
-    for (int r = 0; r < RPL; ++r) {
-        act[r] = live[r] && (z[r] > s[r]);
-        nact += act[r] ? 1 : 0;
-        w.d[lane + 32 * r] = act[r] ? 1.0 : 0.0;
-    }
-    nact = __reduce_add_sync(FULL_MASK, nact);
-    __syncwarp();
-    res.x = xs;
-    res.fun = f0;
-    if (PB_UNI(nact == 0)) return res;
-    form_normal_matrix(w, mk, n, lane);
-    {
-        const double dg = own ? w.M[lane * w.LDM + lane] : 0.0;
-        const double reg = 1e-9 * fmax(1.0, warp_max(dg));
-        if (own) w.M[lane * w.LDM + lane] = dg + reg;
-        __syncwarp();
-    }
-    cholesky(w, n, lane);
-    double xp = xs;
-    double gxp[1][RPL];
-    for (int round = 0; round < 4; ++round) {
-        if (lane < NP) w.u[lane] = own ? xp : 0.0;
-        __syncwarp();
-        rows_times<RPL, 1>(w, n, 0, lane, gxp);
-        if (round == 3) break;
-#pragma unroll
-        for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = act[r] ? h[r] - gxp[0][r] : 0.0;
-        __syncwarp();
-        gt_times_slots(w, mk, n, 1, lane);
-        double dxp[1] = {own ? w.R[lane] : 0.0};
-        chol_solve<1>(w, n, lane, dxp);
-        xp += dxp[0];
-    }
-    double slack = 1e300;
-#pragma unroll
-    for (int r = 0; r < RPL; ++r)
-        if (live[r]) slack = fmin(slack, h[r] - gxp[0][r]);
-    slack = warp_min(slack);
-    const double f1 = warp_sum(c_orig * xp);
-    const bool accept = (slack >= -1e-9 * fmax(1.0, hmax)) && (fabs(f1 - f0) <= 1e-6 * fmax(1.0, fabs(f0)));
-    if (accept) { res.x = xp; res.fun = f1; }
     return res;
 }
 
