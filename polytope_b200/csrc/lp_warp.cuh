@@ -284,6 +284,7 @@ __device__ __forceinline__ bool polish_active_set(const WarpScratch& w, int mk, 
 #pragma unroll
     for (int r = 0; r < RPL; ++r) y[r] = 0.0;
     const double te = 1.0 / tau;
+    double ymin = 1e300, ymax = 0.0;
     bool ok = true;
     // rounds 0-2: projection; round 3: checks (+ start of the certificate); 4, 5: refinement
 #pragma unroll 1
@@ -293,6 +294,15 @@ __device__ __forceinline__ bool polish_active_set(const WarpScratch& w, int mk, 
         }
         __syncwarp();
         rows_times<RPL, 1>(w, n, 0, lane, gxp);
+        if (round == 1 || round == 2) {
+            // the projection usually lands on the face after one or two rounds: skip the rest
+            double t = 0.0;
+#pragma unroll
+            for (int r = 0; r < RPL; ++r)
+                if (act[r]) t = fmax(t, fabs(h[r] - gxp[0][r]));
+            t = warp_max(t);
+            if (PB_UNI(t <= 1e-13 * fmax(1.0, hmax))) round = 3;
+        }
         if (round < 3) {
 #pragma unroll
             for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = act[r] ? h[r] - gxp[0][r] : 0.0;
@@ -317,25 +327,23 @@ __device__ __forceinline__ bool polish_active_set(const WarpScratch& w, int mk, 
                 w.V[lane + 32 * r] = y[r];
             }
         } else {
-            double ymin = 1e300, ymax = 0.0;
+            ymin = 1e300; ymax = 0.0;
 #pragma unroll
             for (int r = 0; r < RPL; ++r) {
                 if (act[r]) { y[r] -= gxp[0][r]; ymin = fmin(ymin, y[r]); ymax = fmax(ymax, y[r]); }
                 w.V[lane + 32 * r] = y[r];
             }
-            if (round == 5) {
-                __syncwarp();
-                gt_times_slots(w, mk, n, 1, lane);
-                const double rd = own ? fabs(w.R[lane] + c_orig) : 0.0;      // |G_B'y + c|
-                const double rdmax = warp_max(rd);
-                ymin = warp_min(ymin);
-                ymax = warp_max(ymax);
-                ok = rdmax <= 1e-9 * nc && ymin >= -1e-9 * fmax(1.0, ymax);
-                break;
-            }
         }
         __syncwarp();
         gt_times_slots(w, mk, n, 1, lane);
+        if (round >= 4) {
+            // refined multipliers: dual feasible already?  (usually after the first refinement)
+            const double rd = own ? fabs(w.R[lane] + c_orig) : 0.0;      // |G_B'y + c|
+            const double rdmax = warp_max(rd);
+            const double ylo = warp_min(ymin), yhi = warp_max(ymax);
+            ok = rdmax <= 1e-9 * nc && ylo >= -1e-9 * fmax(1.0, yhi);
+            if (PB_UNI(ok || round == 5)) break;
+        }
         double rhs[1] = {own ? (round < 3 ? w.R[lane] : w.R[lane] + c_orig) : 0.0};
         chol_solve<1>(w, n, lane, rhs);
         if (round < 3) xp += rhs[0];

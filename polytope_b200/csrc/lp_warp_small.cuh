@@ -350,6 +350,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
 #pragma unroll
     for (int r = 0; r < RPL; ++r) { act[r] = false; y[r] = 0.0; }
     double f0 = 0.0, xp = 0.0;            // xp: lane-owned polished point
+    double ymin = 1e300, ymax = 0.0;      // range of the certificate multipliers on the active rows
     __syncwarp();
 
 #pragma unroll 1
@@ -388,6 +389,15 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
 #pragma unroll
             for (int r = 0; r < RPL; ++r) { rz[r] = 0.0; d[r] = 0.0; sinv[r] = 0.0; zinv[r] = 0.0; }
             bool fallback = false;
+            if (round == 1 || round == 2) {
+                // the projection usually lands on the face after one or two rounds: skip the rest
+                double t = 0.0;
+#pragma unroll
+                for (int r = 0; r < RPL; ++r)
+                    if (act[r]) t = fmax(t, fabs(h[r] - gx[r]));
+                t = warp_max(t);
+                if (PB_UNI(t <= 1e-13 * fmax(1.0, hmax))) round = 3;
+            }
             if (round < 3) {
                 // projection rounds: residual of the active rows at the current point
 #pragma unroll
@@ -422,27 +432,11 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                 }
             } else {
                 // certificate refinement: gx = G u with u = (G_B'G_B)^-1 (G_B'y + c)
-                double ymin = 1e300, ymax = 0.0;
+                ymin = 1e300; ymax = 0.0;
 #pragma unroll
                 for (int r = 0; r < RPL; ++r) {
                     if (act[r]) { y[r] -= gx[r]; ymin = fmin(ymin, y[r]); ymax = fmax(ymax, y[r]); }
                     w.V[lane + 32 * r] = y[r];
-                }
-                if (round == 5) {
-                    __syncwarp();
-                    s_gt_times_slots(w, mk, 1, lane);
-                    const double rd = own ? fabs(w.R[lane] + cl0) : 0.0;      // |G_B'y + c|
-                    const double rdmax = warp_max(rd);
-                    ymin = warp_min(ymin);
-                    ymax = warp_max(ymax);
-                    if (PB_UNI(rdmax <= 1e-9 * sqrt(nc2) && ymin >= -1e-9 * fmax(1.0, ymax))) {
-                        // primal feasible, dual feasible, complementary: optimal
-                        res.status = ST_OPTIMAL;
-                        res.x = xp;
-                        res.fun = warp_sum(cl0 * xp);
-                        break;
-                    }
-                    fallback = true;
                 }
             }
             if (PB_UNI(fallback)) {
@@ -455,6 +449,26 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
         }
         __syncwarp();
         s_gt_times_slots(w, mk, phase == 0 ? 3 : 1, lane);
+        if (phase == 1 && round >= 4) {
+            // refined multipliers: dual feasible already?  (usually after the first refinement)
+            const double rd = own ? fabs(w.R[lane] + cl0) : 0.0;      // |G_B'y + c|
+            const double rdmax = warp_max(rd);
+            const double ylo = warp_min(ymin), yhi = warp_max(ymax);
+            if (PB_UNI(rdmax <= 1e-9 * sqrt(nc2) && ylo >= -1e-9 * fmax(1.0, yhi))) {
+                // primal feasible, dual feasible, complementary: optimal
+                res.status = ST_OPTIMAL;
+                res.x = xp;
+                res.fun = warp_sum(cl0 * xp);
+                break;
+            }
+            if (round == 5) {
+                // not certified: resume the interior-point iterations from the untouched iterate
+                phase = 0; early = false;
+                if (own) Xx[lane] = xl;
+                __syncwarp();
+                continue;
+            }
+        }
         const bool refactor = (phase == 0) || (round == 0);
         if (refactor) s_normal_matrix(w, mk, lane);
         double rxl = 0.0, rt = 0.0, mu = 0.0, tinv = 1.0;
