@@ -301,7 +301,7 @@ def run_gpu(args):
         'e2e': {'value': e2e_value, 'unit': 'LPs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'roofline': {'bound': 'hbm', 'kernel': 'lp_kernel<1, RowLP> (reduce row LPs)', 'achieved': achieved,
+        'roofline': {'bound': 'hbm', 'kernel': 'lp_kernel_small<1, RowLP> (reduce row LPs)', 'achieved': achieved,
                      'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
                      'peak_source': peak_src, 'kernel_ms': row_ms, 'algorithmic_bytes': alg_bytes,
                      'kernel_share_of_step': row_ms / (ms_dev / args.steps),
