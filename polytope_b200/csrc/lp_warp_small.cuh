@@ -194,43 +194,36 @@ __device__ __forceinline__ void load_vec(const double* src, double (&v)[NS]) {
     }
 }
 
-// ---- replicated solve of (L L') y = r for the NR right-hand sides stored as
-// consecutive 8-vectors at X; solutions overwrite them.  L is read by broadcast.
-// All NR systems are always solved (a caller with fewer right-hand sides passes
-// zeros): a run-time count cost one register move per DFMA (profiles/r01e_*).
+// ---- replicated solve of (L L') y = r for the NR (1 or 2) right-hand sides stored
+// as consecutive 8-vectors at X; solutions overwrite them.  L is read by broadcast.
+// With two right-hand sides each half warp solves one of them, so the instruction
+// count is that of a single solve (a caller with one right-hand side passes zeros
+// as the second: a run-time count cost one register move per DFMA, profiles/r01e_*).
 template <int NR>
 __device__ __forceinline__ void s_solve(const double* Ms, double* X, int lane) {
-    double a[NR][NS];
-#pragma unroll
-    for (int v = 0; v < NR; ++v) load_vec(X + v * NS, a[v]);
+    double* mine = X + (NR == 2 ? (lane >> 4) * NS : 0);
+    double a[NS];
+    load_vec(mine, a);
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         double row[NS];
         load_vec(Ms + k * NS, row);
+        a[k] *= row[k];
 #pragma unroll
-        for (int v = 0; v < NR; ++v) {
-            a[v][k] *= row[k];
-#pragma unroll
-            for (int i = k + 1; i < NS; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
-        }
+        for (int i = k + 1; i < NS; ++i) a[i] = fma(-row[i], a[k], a[i]);
     }
 #pragma unroll
     for (int k = NS - 1; k >= 0; --k) {
         double row[NS];
         load_vec(Ms + k * NS, row);
+        a[k] *= row[k];
 #pragma unroll
-        for (int v = 0; v < NR; ++v) {
-            a[v][k] *= row[k];
-#pragma unroll
-            for (int i = 0; i < k; ++i) a[v][i] = fma(-row[i], a[v][k], a[v][i]);
-        }
+        for (int i = 0; i < k; ++i) a[i] = fma(-row[i], a[k], a[i]);
     }
     __syncwarp();
-    // identical values in every lane: all lanes store (same address, same data)
+    // identical values in every lane of a half warp: all lanes store (same address, same data)
 #pragma unroll
-    for (int v = 0; v < NR; ++v)
-#pragma unroll
-        for (int j = 0; j < NS; j += 2) *reinterpret_cast<double2*>(X + v * NS + j) = make_double2(a[v][j], a[v][j + 1]);
+    for (int j = 0; j < NS; j += 2) *reinterpret_cast<double2*>(mine + j) = make_double2(a[j], a[j + 1]);
     __syncwarp();
 }
 
