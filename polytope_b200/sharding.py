@@ -54,3 +54,33 @@ def reduce_batch_sharded(A, b, group=None, abs_tol=1e-7, normalize=True):
         res = engine.reduce_batch(Al, bl, abs_tol=abs_tol, normalize=normalize, want_A=False)
         return res.keep, res.flags, res.n_lp
     return sharded_map(local, A.shape[0], group)
+
+
+def pair_block(n_cells, lo, hi, device='cpu'):
+    """Pairs lo..hi-1 of the enumeration t -> (i, j), j < i, t = i(i-1)/2 + j, that
+    find_adjacent_regions walks (prop2partition.py:57-61): int32 tensors (i, j)."""
+    t = torch.arange(lo, hi, dtype=torch.int64, device=device)
+    i = torch.floor((1.0 + torch.sqrt(1.0 + 8.0 * t.double())) * 0.5).to(torch.int64)
+    i = torch.where(i * (i - 1) // 2 > t, i - 1, i)
+    i = torch.where((i + 1) * i // 2 <= t, i + 1, i)
+    j = t - i * (i - 1) // 2
+    assert n_cells < 2 or hi <= n_cells * (n_cells - 1) // 2
+    return i.to(torch.int32), j.to(torch.int32)
+
+
+def adjacency_sharded(A, b, group=None, abs_tol=1e-7):
+    """cfg5: is_adjacent over all pairs j < i of `ncell` cells (prop2partition.py:46-63),
+    the pair index range split across the ranks of `group`.  Every rank holds all
+    cells (they are tiny) and enumerates its own pair range; one all-gather of the
+    uint8 flags.  -> flags uint8[ncell (ncell - 1) / 2] on every rank."""
+    from polytope_b200 import engine
+    ncell = A.shape[0]
+    T = ncell * (ncell - 1) // 2
+    Ad = torch.as_tensor(A).to('cuda')
+    bd = torch.as_tensor(b).to('cuda')
+
+    def local(lo, hi):
+        pi, pj = pair_block(ncell, lo, hi, device='cuda')
+        adj, _, _ = engine.adjacent_pairs(Ad, bd, pi, pj, abs_tol=abs_tol)
+        return (adj,)
+    return sharded_map(local, T, group)[0]

@@ -160,6 +160,13 @@ def test_adjacency_grid_matches_reference_golden(golden, tag):
     cells = [pb.Polytope(A[i], b[i]) for i in range(len(A))]
     adj = pb.adjacency_matrix(cells)
     assert np.array_equal(adj, g[tag + '_adj'])
+    # the multi-GPU entry (pair range split over the ranks; one rank here) gives the same flags
+    from polytope_b200 import sharding
+    An = np.array([c.A for c in cells])
+    bn = np.array([c.b for c in cells])
+    flags = sharding.adjacency_sharded(An, bn).cpu().numpy()
+    i, j = np.tril_indices(len(cells), -1)
+    assert np.array_equal(flags, g[tag + '_adj'][i, j])
 
 
 @pytest.mark.parametrize('origin,cell', [(0.0, 1.0), (1e3, 1.0), (-3e3, 0.01), (0.0, 1e3), (1e5, 1.0)])

@@ -22,6 +22,21 @@ def test_shard_bounds_cover_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_pair_block_enumeration_matches_tril_order():
+    """cfg5 sharding: rank-local pair ranges reproduce find_adjacent_regions' order."""
+    for n in (2, 3, 10, 1024, 1415):
+        T = n * (n - 1) // 2
+        ii, jj = np.tril_indices(n, -1)
+        for world in (1, 2, 8):
+            got_i, got_j = [], []
+            for r in range(world):
+                lo, hi = sharding.shard_bounds(T, r, world)
+                i, j = sharding.pair_block(n, lo, hi)
+                got_i.append(i.numpy())
+                got_j.append(j.numpy())
+            assert np.array_equal(np.concatenate(got_i), ii) and np.array_equal(np.concatenate(got_j), jj)
+
+
 def _worker(rank, world, port, n_items, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
