@@ -139,19 +139,23 @@ class ReduceResult(object):
 
     def keep_lists(self):
         keep = np.asarray(self.keep.cpu() if isinstance(self.keep, torch.Tensor) else self.keep)
-        m = self.b.shape[1]
+        m = self.b.shape[1] if self.b is not None else 64
         bits = (keep.astype(np.uint64)[:, None] >> np.arange(m, dtype=np.uint64)) & np.uint64(1)
         return [np.nonzero(row)[0].tolist() for row in bits]
 
 
-def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True):
+def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True, want_b=True):
     """reduce(Polytope(A[p], b[p])) for every p (polytope.py:1053-1163).
 
     normalize=False reproduces reduce(poly) on rows that a constructor already
-    normalised (poly.A, poly.b are used as they are).
+    normalised (poly.A, poly.b are used as they are).  For host-resident batches
+    want_A / want_b = False skip the device-to-host copies of the row data (A; b,
+    r, xc) when only the keep masks, flags and LP counts are wanted.
     """
     _require_cuda()
     lib = _capi.lib()
+    if _is_host(A) and len(A) >= 2 * PIPELINE_MIN_CHUNK:
+        return _reduce_batch_host_pipelined(A, b, m_rows, abs_tol, normalize, want_A, want_b)
     A, host = _dev(A)
     b, _ = _dev(b)
     P, m, d = A.shape
@@ -177,6 +181,71 @@ def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True
     outs = _out(host, *outs)
     res.keep, res.flags, res.r, res.xc, res.b, res.n_lp, res.lp_iters = outs[:7]
     res.A = outs[7] if want_A else None
+    return res
+
+
+PIPELINE_MIN_CHUNK = 1024      # polytopes per chunk below which pipelining does not pay
+PIPELINE_CHUNKS = int(__import__('os').environ.get('PB200_PIPELINE_CHUNKS', '2'))
+_pinned = {}
+_streams = []
+
+
+def _is_host(x):
+    return isinstance(x, np.ndarray) or (isinstance(x, torch.Tensor) and not x.is_cuda)
+
+
+def _pinned_buffer(tag, shape, dtype):
+    """Reusable pinned host buffer (cudaHostAlloc is far too slow to do per call)."""
+    key = (tag, tuple(shape), dtype)
+    buf = _pinned.get(key)
+    if buf is None:
+        buf = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        _pinned[key] = buf
+    return buf
+
+
+def _reduce_batch_host_pipelined(A, b, m_rows, abs_tol, normalize, want_A, want_b):
+    """reduce_batch for host-resident batches: the batch is cut into chunks that
+    alternate between two CUDA streams, so the H2D copy of chunk k+1 and the D2H
+    of chunk k-1 overlap the kernels of chunk k.  Results land in pinned host
+    buffers and come back as numpy arrays."""
+    if not _streams:
+        _streams.extend([torch.cuda.Stream(), torch.cuda.Stream()])
+    At = torch.as_tensor(A)
+    bt = torch.as_tensor(b)
+    if At.dtype != torch.float64 or not At.is_contiguous():
+        At = At.to(torch.float64).contiguous()
+    if bt.dtype != torch.float64 or not bt.is_contiguous():
+        bt = bt.to(torch.float64).contiguous()
+    mt = None if m_rows is None else torch.as_tensor(np.ascontiguousarray(m_rows, dtype=np.int32))
+    P, m, d = At.shape
+    nchunk = max(2, min(PIPELINE_CHUNKS, P // PIPELINE_MIN_CHUNK))
+    bounds = [(P * k // nchunk, P * (k + 1) // nchunk) for k in range(nchunk)]
+    names = ['keep', 'flags', 'n_lp', 'lp_iters'] + (['r', 'xc', 'b'] if want_b else []) + (['A'] if want_A else [])
+    shapes = {'keep': (P,), 'flags': (P,), 'r': (P,), 'xc': (P, d), 'b': (P, m), 'n_lp': (P,), 'lp_iters': (P,),
+              'A': (P, m, d)}
+    dtypes = {'keep': torch.int64, 'flags': torch.int32, 'r': torch.float64, 'xc': torch.float64, 'b': torch.float64,
+              'n_lp': torch.int32, 'lp_iters': torch.int32, 'A': torch.float64}
+    out = {n: _pinned_buffer('reduce_' + n, shapes[n], dtypes[n]) for n in names}
+    cur = torch.cuda.current_stream()
+    keepalive = []
+    for k, (lo, hi) in enumerate(bounds):
+        st = _streams[k % 2]
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            Ad = At[lo:hi].to('cuda', non_blocking=True)
+            bd = bt[lo:hi].to('cuda', non_blocking=True)
+            md = None if mt is None else mt[lo:hi].to('cuda', non_blocking=True)
+            res = reduce_batch(Ad, bd, md, abs_tol=abs_tol, normalize=normalize, want_A=want_A)
+            for n in names:
+                out[n][lo:hi].copy_(getattr(res, n), non_blocking=True)
+            keepalive.append((Ad, bd, md, res))
+    for st in _streams:
+        cur.wait_stream(st)
+    cur.synchronize()
+    res = ReduceResult()
+    for n in ReduceResult.__slots__:
+        setattr(res, n, out[n].numpy().copy() if n in out else None)
     return res
 
 
