@@ -176,6 +176,45 @@ __device__ __forceinline__ int block_compact_pos(BlockScratch& bs, bool flag, in
     return flag ? before + __popc(bal & ((1u << lane) - 1u)) : -1;
 }
 
+// Ordered compaction of a whole index range: emit(pos, f) is called for every
+// f in [0, n) with flag(f) true, positions counted from `base` on.  Each warp
+// walks a contiguous run of 8 x 32 indices per round (coalesced, eight
+// independent evaluations of `flag` in flight), keeps the eight ballots in
+// registers and needs ONE block barrier per 2048 indices for the cross-warp
+// prefix.  The order is deterministic (by warp run, then index).
+template <class Flag, class Emit>
+__device__ __forceinline__ void block_compact_range(BlockScratch& bs, int n, int& base, int& parity, Flag flag, Emit emit) {
+    constexpr int Q = 8;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int c0 = 0; c0 < n; c0 += HT * Q) {
+        unsigned masks[Q];
+        int mine = 0;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int f = c0 + wid * (32 * Q) + 32 * q + lane;
+            const bool fl = f < n && flag(f);
+            masks[q] = __ballot_sync(FULL, fl);
+            mine += __popc(masks[q]);
+        }
+        if (lane == 0) bs.cnt[parity][wid] = mine;
+        __syncthreads();
+        int before = base, total = 0;
+#pragma unroll
+        for (int w = 0; w < HW; ++w) {
+            const int c = bs.cnt[parity][w];
+            if (w < wid) before += c;
+            total += c;
+        }
+        parity ^= 1;
+        base += total;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            if ((masks[q] >> lane) & 1u) emit(before + __popc(masks[q] & ((1u << lane) - 1u)), c0 + wid * (32 * Q) + 32 * q + lane);
+            before += __popc(masks[q]);
+        }
+    }
+}
+
 // ---- ridge hashing ----
 __device__ __forceinline__ int ridge_elem(const int32_t* vid, int cap, int f, int i, int t) {
     return vid[(size_t)(t + (t >= i ? 1 : 0)) * cap + f];
@@ -213,17 +252,16 @@ __device__ __forceinline__ bool facet_plane(const double* __restrict__ X, int ld
     bool used = !row;
     mycol = -1;
     bool ok = true;
+    const unsigned half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        double cand = used ? -1.0 : fabs(a[k]);
-        int who = gl;
-#pragma unroll
-        for (int o = 8; o; o >>= 1) {
-            const double oc = __shfl_xor_sync(FULL, cand, o, 16);
-            const int ow = __shfl_xor_sync(FULL, who, o, 16);
-            if (oc > cand || (oc == cand && ow < who)) { cand = oc; who = ow; }
-        }
-        if (!(cand > 1e-300)) ok = false;
+        // row pivot: largest |a[k]| among the unused rows of this half warp.  The magnitude
+        // (as fp32 bits, order-preserving for non-negative floats) and the lane share one
+        // 32-bit key, so the search is a single warp reduction; ties go to the higher lane.
+        const unsigned key = used ? 0u : ((__float_as_uint(__double2float_rd(fabs(a[k]))) & ~0xfu) | (unsigned)gl) + 16u;
+        const unsigned best = __reduce_max_sync(half_mask, key);
+        if (best < 32u) ok = false;                       // every candidate was (sub)zero
+        const int who = (int)((best - 16u) & 0xfu);
         const double pv = __shfl_sync(FULL, a[k], who, 16);
         const double rinv = 1.0 / pv;
         const double f = (gl == who) ? 0.0 : a[k] * rinv;
@@ -235,10 +273,11 @@ __device__ __forceinline__ bool facet_plane(const double* __restrict__ X, int ld
         if (gl == who) { used = true; mycol = k; }
     }
     // lane that pivoted column k holds x_k = a[D] / a[k]
-    double xk = 0.0;
+    double piv = 1.0;
 #pragma unroll
     for (int k = 0; k < D; ++k)
-        if (mycol == k) xk = a[D] / a[k];
+        if (mycol == k) piv = a[k];
+    const double xk = mycol >= 0 ? a[D] / piv : 0.0;
     double s = xk * xk;
 #pragma unroll
     for (int o = 8; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o, 16);
@@ -432,14 +471,13 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
 #pragma unroll
         for (int c = 0; c < D; ++c) p[c] = sh_p[c];
         int nV = 0;
-        for (int f0 = 0; f0 < hi; f0 += HT) {
-            const int f = f0 + tid;
-            bool v = false;
-            if (f < hi && w.state[f] == 1) v = facet_dist(w, cap, d, f, p) > a.tol;
-            if (f < hi) w.vis[f] = v ? 1 : 0;
-            const int pos = block_compact_pos(bs, v, nV, parity);
-            if (v) w.vis_list[pos] = f;
-        }
+        block_compact_range(bs, hi, nV, parity,
+                            [&](int f) {
+                                const bool v = w.state[f] == 1 && facet_dist(w, cap, d, f, p) > a.tol;
+                                w.vis[f] = v ? 1 : 0;
+                                return v;
+                            },
+                            [&](int pos, int f) { w.vis_list[pos] = f; });
         __syncthreads();
         // (c) horizon: ridges of visible facets that occur once
         const unsigned tcap = table_cap(cap, d);
@@ -466,28 +504,25 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         }
         __syncthreads();
         int nH = 0;
-        for (int t0 = 0; t0 < items; t0 += HT) {
-            const int t = t0 + tid;
-            bool horizon = false;
-            int item = 0;
-            if (t < items) {
-                const int f = w.vis_list[t / d], i = t % d;
-                item = f * d + i;
-                uint32_t slot = ridge_hash(w.vid, cap, d, f, i) & (tsize - 1);
-                for (unsigned probe = 0; probe < tsize; ++probe) {
-                    const uint32_t cur = w.table[slot];
-                    if (cur == 0u) break;
-                    const uint32_t other = (cur & ~DUP_BIT) - 1u;
-                    if (other == (uint32_t)item || ridge_equal(w.vid, cap, d, f, i, (int)(other / d), (int)(other % d))) {
-                        horizon = !(cur & DUP_BIT);
-                        break;
-                    }
-                    slot = (slot + 1) & (tsize - 1);
-                }
-            }
-            const int pos = block_compact_pos(bs, horizon, nH, parity);
-            if (horizon && pos < cap) w.hor_list[pos] = item;
-        }
+        block_compact_range(bs, items, nH, parity,
+                            [&](int t) {
+                                const int f = w.vis_list[t / d], i = t % d;
+                                const int item = f * d + i;
+                                uint32_t slot = ridge_hash(w.vid, cap, d, f, i) & (tsize - 1);
+                                for (unsigned probe = 0; probe < tsize; ++probe) {
+                                    const uint32_t cur = w.table[slot];
+                                    if (cur == 0u) break;
+                                    const uint32_t other = (cur & ~DUP_BIT) - 1u;
+                                    if (other == (uint32_t)item ||
+                                        ridge_equal(w.vid, cap, d, f, i, (int)(other / d), (int)(other % d)))
+                                        return !(cur & DUP_BIT);
+                                    slot = (slot + 1) & (tsize - 1);
+                                }
+                                return false;
+                            },
+                            [&](int pos, int t) {
+                                if (pos < cap) w.hor_list[pos] = w.vis_list[t / d] * d + t % d;
+                            });
         __syncthreads();
         // (d) slots for the cone of new facets: recycled ones first, then fresh ones
         const int from_free = min(nH, nfree);
@@ -509,16 +544,12 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         // (f) orphaned outside points go to the first new facet (in cone order) they are
         // outside of (quickhull.py:316-336): all (facet, orphan) pairs in parallel
         int nO = 0;
-        for (int j0 = 0; j0 < n; j0 += HT) {
-            const int j = j0 + tid;
-            bool orphan = false;
-            if (j < n) {
-                const int o = w.owner[j];
-                orphan = o >= 0 && w.vis[o];
-            }
-            const int pos = block_compact_pos(bs, orphan, nO, parity);
-            if (orphan) { w.orph[pos] = j; w.cand[j] = 0x7fffffff; }
-        }
+        block_compact_range(bs, n, nO, parity,
+                            [&](int j) {
+                                const int o = w.owner[j];
+                                return o >= 0 && w.vis[o] != 0;
+                            },
+                            [&](int pos, int j) { w.orph[pos] = j; w.cand[j] = 0x7fffffff; });
         __syncthreads();
         if (nO > 0) {
             const long long pairs = (long long)nH * nO;
@@ -563,12 +594,8 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
 
     // ---- output: live facets, b = off + n . centre (quickhull.py:348-359) ----
     int nF = 0;
-    for (int f0 = 0; f0 < hi; f0 += HT) {
-        const int f = f0 + tid;
-        const bool live = f < hi && w.state[f] == 1;
-        const int pos = block_compact_pos(bs, live, nF, parity);
-        if (live) w.vis_list[pos] = f;
-    }
+    block_compact_range(bs, hi, nF, parity, [&](int f) { return w.state[f] == 1; },
+                        [&](int pos, int f) { w.vis_list[pos] = f; });
     __syncthreads();
     if (tid == 0) {
         const unsigned long long o = atomicAdd(a.out_used, (unsigned long long)nF);
@@ -594,7 +621,7 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
 }
 
 template <int D>
-__global__ void __launch_bounds__(HT) hull_kernel(const HullArgs a) {
+__global__ void __launch_bounds__(HT, 3) hull_kernel(const HullArgs a) {
     extern __shared__ __align__(16) double smem_x[];
     __shared__ BlockScratch bs;
     __shared__ double sh_p[HULL_MAX_D], sh_c[HULL_MAX_D], sh_q[HULL_MAX_D * HULL_MAX_D];
@@ -624,7 +651,7 @@ static int launch_hull(const HullArgs& a, int grid, size_t smem, cudaStream_t st
 static int hull_grid(int H) {
     const int sms = sm_count();
     if (!sms) return 0;
-    const int g = 2 * sms;
+    const int g = 3 * sms;
     return H < g ? H : g;
 }
 static int hull_x_in_smem(int Nmax, int d) { return (size_t)Nmax * d * sizeof(double) <= 96 * 1024 ? 1 : 0; }
