@@ -106,13 +106,17 @@ __device__ PB200_REDUCE_INLINE void warp_sum2(double& a, double& b) {
 }
 
 // ---- one DMMA tile: R[slot][j] = sum_i G[i][j] V[slot][i] ----
-__device__ __forceinline__ void s_gt_times_slots(const SmallScratch& w, int mk, int nslots, int lane) {
+// The k-loops of both DMMA passes always cover all 32*RPL staged rows (rows >= m are
+// zero in G, V and d), so they unroll completely: no loop branches in the hot path.
+template <int RPL>
+__device__ __forceinline__ void s_gt_times_slots(const SmallScratch& w, int nslots, int lane) {
     const int q = lane >> 2, t = lane & 3;
     double c0 = 0.0, c1 = 0.0;
     const bool cb = q < nslots;
     const double* ga = w.G + q * w.MP + t;
-    const double* vb = w.V + q * w.MP + t;
-    for (int i0 = 0; i0 < mk; i0 += 4) {
+    const double* vb = w.V + (cb ? q : 0) * w.MP + t;
+#pragma unroll
+    for (int i0 = 0; i0 < 32 * RPL; i0 += 4) {
         const double a = ga[i0];
         const double b = cb ? vb[i0] : 0.0;
         dmma884(c0, c1, a, b);
@@ -125,12 +129,14 @@ __device__ __forceinline__ void s_gt_times_slots(const SmallScratch& w, int mk, 
 }
 
 // ---- one DMMA tile: M = G' diag(d) G (full 8x8, row-major) ----
-__device__ __forceinline__ void s_normal_matrix(const SmallScratch& w, int mk, int lane) {
+template <int RPL>
+__device__ __forceinline__ void s_normal_matrix(const SmallScratch& w, int lane) {
     const int q = lane >> 2, t = lane & 3;
     double c0 = 0.0, c1 = 0.0;
     const double* gq = w.G + q * w.MP + t;
     const double* dd = w.d + t;
-    for (int i0 = 0; i0 < mk; i0 += 4) {
+#pragma unroll
+    for (int i0 = 0; i0 < 32 * RPL; i0 += 4) {
         const double g = gq[i0];
         dmma884(c0, c1, g * dd[i0], g);
     }
@@ -272,7 +278,7 @@ __device__ __noinline__ bool s_objective_leaves_range(const SmallScratch& w, int
 #pragma unroll
     for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = w.d[lane + 32 * r] * gu[r];
     __syncwarp();
-    s_gt_times_slots(w, mk, 1, lane);
+    s_gt_times_slots<RPL>(w, 1, lane);
     const double back = own ? w.R[lane] : 0.0;
     const double rmax = warp_max(fabs(cl - back)), cmax = warp_max(fabs(cl));
     __syncwarp();
@@ -441,7 +447,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             }
         }
         __syncwarp();
-        s_gt_times_slots(w, mk, phase == 0 ? 3 : 1, lane);
+        s_gt_times_slots<RPL>(w, phase == 0 ? 3 : 1, lane);
         if (phase == 1 && round >= 4) {
             // refined multipliers: dual feasible already?  (usually after the first refinement)
             const double rd = own ? fabs(w.R[lane] + cl0) : 0.0;      // |G_B'y + c|
@@ -463,7 +469,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             }
         }
         const bool refactor = (phase == 0) || (round == 0);
-        if (refactor) s_normal_matrix(w, mk, lane);
+        if (refactor) s_normal_matrix<RPL>(w, lane);
         double rxl = 0.0, rt = 0.0, mu = 0.0, tinv = 1.0;
         if (phase == 0) {
             const double gzl = own ? w.R[lane] : 0.0;          // (G'z)_lane
@@ -625,7 +631,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                     w.V[lane + 32 * r] = d[r] * qc[r];
                 }
                 __syncwarp();
-                s_gt_times_slots(w, mk, 1, lane);
+                s_gt_times_slots<RPL>(w, 1, lane);
             } else {
                 // combined direction and step
                 double hz2 = 0.0;

@@ -47,7 +47,7 @@ def test_qhull_matches_reference_golden(golden):
     assert len(pc.qhull(flat).A) == 0                           # not full-dimensional
 
 
-@pytest.mark.parametrize('n,d', [(500, 2), (2000, 3), (300, 4), (120, 6), (60, 8), (40, 10)])
+@pytest.mark.parametrize('n,d', [(500, 2), (2000, 3), (6000, 3), (300, 4), (120, 6), (60, 8), (40, 10)])
 def test_hull_batch_vs_qhull_oracle(n, d):
     from polytope_b200 import engine
     from oracle import polytope_oracle as orc
