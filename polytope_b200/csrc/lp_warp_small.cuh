@@ -106,21 +106,25 @@ __device__ PB200_REDUCE_INLINE void warp_sum2(double& a, double& b) {
 }
 
 // ---- one DMMA tile: R[slot][j] = sum_i G[i][j] V[slot][i] ----
-// The k-loops of both DMMA passes always cover all 32*RPL staged rows (rows >= m are
-// zero in G, V and d), so they unroll completely: no loop branches in the hot path.
+// The k-loops of both DMMA passes cover whole 32-row blocks of the staged rows (rows >= m
+// are zero in G, V and d), so they unroll completely: no loop branches in the hot path.
 template <int RPL>
-__device__ __forceinline__ void s_gt_times_slots(const SmallScratch& w, int nslots, int lane) {
+__device__ __forceinline__ void s_gt_times_slots(const SmallScratch& w, int mk, int nslots, int lane) {
     const int q = lane >> 2, t = lane & 3;
     double c0 = 0.0, c1 = 0.0;
     const bool cb = q < nslots;
     const double* ga = w.G + q * w.MP + t;
     const double* vb = w.V + (cb ? q : 0) * w.MP + t;
 #pragma unroll
-    for (int i0 = 0; i0 < 32 * RPL; i0 += 4) {
-        const double a = ga[i0];
-        const double b = cb ? vb[i0] : 0.0;
-        dmma884(c0, c1, a, b);
-    }
+    for (int blk = 0; blk < RPL; ++blk)
+        if (blk == 0 || mk > 32 * blk) {          // whole 32-row blocks: one uniform test per block
+#pragma unroll
+            for (int i0 = 32 * blk; i0 < 32 * blk + 32; i0 += 4) {
+                const double a = ga[i0];
+                const double b = cb ? vb[i0] : 0.0;
+                dmma884(c0, c1, a, b);
+            }
+        }
     if (t < 2) {
         w.R[(2 * t) * NS + q] = c0;
         w.R[(2 * t + 1) * NS + q] = c1;
@@ -130,16 +134,20 @@ __device__ __forceinline__ void s_gt_times_slots(const SmallScratch& w, int nslo
 
 // ---- one DMMA tile: M = G' diag(d) G (full 8x8, row-major) ----
 template <int RPL>
-__device__ __forceinline__ void s_normal_matrix(const SmallScratch& w, int lane) {
+__device__ __forceinline__ void s_normal_matrix(const SmallScratch& w, int mk, int lane) {
     const int q = lane >> 2, t = lane & 3;
     double c0 = 0.0, c1 = 0.0;
     const double* gq = w.G + q * w.MP + t;
     const double* dd = w.d + t;
 #pragma unroll
-    for (int i0 = 0; i0 < 32 * RPL; i0 += 4) {
-        const double g = gq[i0];
-        dmma884(c0, c1, g * dd[i0], g);
-    }
+    for (int blk = 0; blk < RPL; ++blk)
+        if (blk == 0 || mk > 32 * blk) {
+#pragma unroll
+            for (int i0 = 32 * blk; i0 < 32 * blk + 32; i0 += 4) {
+                const double g = gq[i0];
+                dmma884(c0, c1, g * dd[i0], g);
+            }
+        }
     *reinterpret_cast<double2*>(w.M + q * NS + 2 * t) = make_double2(c0, c1);
     __syncwarp();
 }
@@ -278,7 +286,7 @@ __device__ __noinline__ bool s_objective_leaves_range(const SmallScratch& w, int
 #pragma unroll
     for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = w.d[lane + 32 * r] * gu[r];
     __syncwarp();
-    s_gt_times_slots<RPL>(w, 1, lane);
+    s_gt_times_slots<RPL>(w, mk, 1, lane);
     const double back = own ? w.R[lane] : 0.0;
     const double rmax = warp_max(fabs(cl - back)), cmax = warp_max(fabs(cl));
     __syncwarp();
@@ -447,7 +455,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             }
         }
         __syncwarp();
-        s_gt_times_slots<RPL>(w, phase == 0 ? 3 : 1, lane);
+        s_gt_times_slots<RPL>(w, mk, phase == 0 ? 3 : 1, lane);
         if (phase == 1 && round >= 4) {
             // refined multipliers: dual feasible already?  (usually after the first refinement)
             const double rd = own ? fabs(w.R[lane] + cl0) : 0.0;      // |G_B'y + c|
@@ -469,7 +477,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             }
         }
         const bool refactor = (phase == 0) || (round == 0);
-        if (refactor) s_normal_matrix<RPL>(w, lane);
+        if (refactor) s_normal_matrix<RPL>(w, mk, lane);
         double rxl = 0.0, rt = 0.0, mu = 0.0, tinv = 1.0;
         if (phase == 0) {
             const double gzl = own ? w.R[lane] : 0.0;          // (G'z)_lane
@@ -631,7 +639,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                     w.V[lane + 32 * r] = d[r] * qc[r];
                 }
                 __syncwarp();
-                s_gt_times_slots<RPL>(w, 1, lane);
+                s_gt_times_slots<RPL>(w, mk, 1, lane);
             } else {
                 // combined direction and step
                 double hz2 = 0.0;
