@@ -44,7 +44,8 @@ constexpr int LP_MAX_N = 32;            // columns (n-vectors are lane-owned)
 constexpr double LP_FEAS_TOL = 1e-9;
 constexpr double LP_GAP_TOL = 1e-9;
 constexpr double LP_STEP = 0.99;
-constexpr double LP_EARLY_TOL = 1e-3;      // tolerance at which the certified polish is first tried
+constexpr double LP_EARLY_TOL = 1e-2;      // tolerance at which the certified polish is first tried
+constexpr double LP_EARLY_NEXT = 1e-2;     // a failed attempt is repeated once the residuals shrank by this factor
 constexpr int NSLOT = 4;                // vector slots of a G'V pass
 
 // scipy.optimize.linprog status codes (polytope/solvers.py:92-93)
@@ -383,7 +384,8 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
     hmax = warp_max(hmax);
     double nc = fmax(1.0, sqrt(warp_sum(c * c)));
     double x = 0.0, tau = 1.0, kap = 1.0;
-    bool lineal = false, tried = false;
+    bool lineal = false;
+    double etol = LP_EARLY_TOL;            // tolerance of the next certified-polish attempt
     LpResult res;
     res.status = ST_ITER_LIMIT; res.iters = 0; res.x = 0.0; res.fun = 0.0;
 
@@ -439,11 +441,10 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
         // polish there and accept it only with a full optimality certificate (primal
         // feasible, active rows tight, y >= 0 with G_B'y + c = 0); otherwise keep
         // iterating to the tight tolerance (same scheme as lp_warp_small.cuh).
-        const bool loosely = !tried && !lineal && pres <= LP_EARLY_TOL && dres <= LP_EARLY_TOL &&
-                             (gap <= LP_EARLY_TOL || relgap <= LP_EARLY_TOL);
+        const bool loosely = etol > 1e-7 && !lineal && pres <= etol && dres <= etol && (gap <= etol || relgap <= etol);
         if (PB_UNI(converged || loosely)) {
             if (PB_UNI(converged && lineal)) { res.status = ST_UNBOUNDED; break; }
-            tried = true;
+            etol *= LP_EARLY_NEXT;
             double xp, fp;
             const double xs = x / tau;
             const bool ok = polish_active_set<RPL>(w, mk, n, lane, own, c_orig, nc, hmax, h, live, s, z, tau, xs, !converged, xp, fp);

@@ -351,7 +351,8 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
     SmallResult res;
     res.status = ST_ITER_LIMIT; res.iters = 0; res.fun = 0.0; res.x = 0.0;
     int phase = 0, round = 0, it = 0;     // phase 0: interior point, 1: polish (+ certificate)
-    bool early = false, tried = false;    // early: polish attempted at the loose tolerance
+    bool early = false;                   // early: polish attempted at a loose tolerance
+    double etol = LP_EARLY_TOL;           // tolerance of the next certified-polish attempt
     bool act[RPL];
     double y[RPL];                        // dual certificate on the active rows
 #pragma unroll
@@ -500,13 +501,12 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             // try the polish there and accept it only with a full optimality
             // certificate (primal feasible, active rows tight, y >= 0 with
             // G_B'y + c = 0); otherwise keep iterating to the tight tolerance.
-            const bool loosely = !tried && !lineal &&
-                                 rz2 * t2 <= LP_EARLY_TOL * LP_EARLY_TOL * nh2 && rx2 * t2 <= LP_EARLY_TOL * LP_EARLY_TOL * nc2 &&
-                                 (gap <= LP_EARLY_TOL || gap <= LP_EARLY_TOL * gapref);
+            const bool loosely = etol > 1e-7 && !lineal && rz2 * t2 <= etol * etol * nh2 && rx2 * t2 <= etol * etol * nc2 &&
+                                 (gap <= etol || gap <= etol * gapref);
             if (PB_UNI(converged || loosely)) {
                 if (PB_UNI(converged && lineal)) { res.status = ST_UNBOUNDED; break; }
                 early = !converged;
-                tried = true;
+                etol *= LP_EARLY_NEXT;
                 // ---- extract, then polish on the active set (see lp_warp.cuh) ----
                 const double te = 1.0 / tau;
                 xp = xl * te;

@@ -598,7 +598,7 @@ __global__ void finalize_kernel(const double* __restrict__ bn, const uint64_t* _
 }
 
 // bounding_box status conventions (polytope.py:1372-1402).  An optimum that
-// sits (to 1e-13) on an axis-aligned facet +-e_j x <= b_i is returned as that
+// sits (to 1e-11) on an axis-aligned facet +-e_j x <= b_i is returned as that
 // facet's b_i exactly: the reference's simplex returns such vertices without
 // rounding, and callers floor()/ceil() the bounds of boxes
 // (enumerate_integral_points, polytope.py:2352-2358).
@@ -622,8 +622,8 @@ __global__ void bbox_resolve_kernel(const int8_t* __restrict__ status, const dou
         for (int k = 0; k < d; ++k) axis = axis && (k == j || row[k] == 0.0);
         if (!axis) continue;
         const double bi = b[(size_t)p * m + i];
-        if (a == 1.0 && su == ST_OPTIMAL && fabs(u - bi) <= 1e-13 * fmax(1.0, fabs(bi))) u = bi;
-        if (a == -1.0 && sl == ST_OPTIMAL && fabs(l + bi) <= 1e-13 * fmax(1.0, fabs(bi))) l = -bi;
+        if (a == 1.0 && su == ST_OPTIMAL && fabs(u - bi) <= 1e-11 * fmax(1.0, fabs(bi))) u = bi;
+        if (a == -1.0 && sl == ST_OPTIMAL && fabs(l + bi) <= 1e-11 * fmax(1.0, fabs(bi))) l = -bi;
     }
     if (sl == ST_UNBOUNDED) l = -inf; else if (sl == ST_INFEASIBLE) l = 0.0; else if (sl != ST_OPTIMAL) l = nan;
     if (su == ST_UNBOUNDED) u = inf; else if (su == ST_INFEASIBLE) u = l; else if (su != ST_OPTIMAL) u = nan;

@@ -16,7 +16,8 @@ MAX_ITER = 60
 FEAS_TOL = 1e-9
 GAP_TOL = 1e-9
 STEP = 0.99
-EARLY_TOL = 1e-3      # loose tolerance at which the certified polish is first tried (small-n kernel)
+EARLY_TOL = 1e-2      # loose tolerance at which the certified polish is first tried
+EARLY_NEXT = 1e-2     # a failed attempt is repeated once the residuals shrank by this factor
 
 
 def _chol_solve_factory(M, n):
@@ -65,7 +66,7 @@ def solve_lp(c, G, h, max_iter=MAX_ITER, polish=True, trace=None, early=True):
     status = 1
     it = 0
     lineal = False
-    tried = False
+    etol = EARLY_TOL
     for it in range(max_iter + 1):
         rx = G.T @ z + c * tau
         rz = G @ x + s - h * tau
@@ -89,11 +90,11 @@ def solve_lp(c, G, h, max_iter=MAX_ITER, polish=True, trace=None, early=True):
         if pres <= FEAS_TOL and dres <= FEAS_TOL and (gap <= GAP_TOL or relgap <= GAP_TOL):
             status = 0
             break
-        if (early and not tried and not lineal and pres <= EARLY_TOL and dres <= EARLY_TOL
-                and (gap <= EARLY_TOL or relgap <= EARLY_TOL)):
+        if (early and etol > 1e-7 and not lineal and pres <= etol and dres <= etol
+                and (gap <= etol or relgap <= etol)):
             # the active set is usually identified long before tight convergence:
             # polish now, accept only with a full optimality certificate
-            tried = True
+            etol *= EARLY_NEXT
             ok, xp = certified_polish(c, G, h, x / tau, s / tau, z / tau)
             if ok:
                 return dict(status=0, x=xp, fun=float(c @ xp), iters=it)
