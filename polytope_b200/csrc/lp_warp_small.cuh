@@ -85,6 +85,18 @@ __device__ __forceinline__ double warp_max_ratio(double v) {
     for (int o = 16; o; o >>= 1) f = fmaxf(f, __shfl_xor_sync(FULL_MASK, f, o));
     return (double)f;
 }
+// five maxima at once, in fp32 rounded up (used for threshold tests only)
+__device__ PB200_REDUCE_INLINE void warp_max5f(float& a, float& b, float& c, float& d, float& e) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ta = __shfl_xor_sync(FULL_MASK, a, o);
+        const float tb = __shfl_xor_sync(FULL_MASK, b, o);
+        const float tc = __shfl_xor_sync(FULL_MASK, c, o);
+        const float td = __shfl_xor_sync(FULL_MASK, d, o);
+        const float te = __shfl_xor_sync(FULL_MASK, e, o);
+        a = fmaxf(a, ta); b = fmaxf(b, tb); c = fmaxf(c, tc); d = fmaxf(d, td); e = fmaxf(e, te);
+    }
+}
 __device__ PB200_REDUCE_INLINE void warp_sum5(double& a, double& b, double& c, double& d, double& e) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -358,17 +370,17 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
 #pragma unroll
     for (int r = 0; r < RPL; ++r) { act[r] = false; y[r] = 0.0; }
     double f0 = 0.0, xp = 0.0;            // xp: lane-owned polished point
-    double ymin = 1e300, ymax = 0.0;      // range of the certificate multipliers on the active rows
     __syncwarp();
 
 #pragma unroll 1
     for (int step = 0; step < LP_MAX_ITER + 16; ++step) {
         // ---- A. rows of G times the current point (x, or x/tau while polishing) ----
-        double gx[RPL], cx;
+        double gx[RPL], gu[RPL], cx;
         {
-            double x[NS], c[NS];
+            double x[NS], c[NS], u[NS];
             load_vec(Xx, x);
-            s_rows_times<RPL>(w, lane, x, gx);
+            load_vec(X2, u);                 // polish: u of the dual refinement (else unused)
+            s_rows_times2<RPL>(w, lane, x, u, gx, gu);
             load_vec(Xc, c);
             cx = dot8(c, x);
         }
@@ -394,88 +406,60 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                 w.V[2 * MP + i] = z[r] - d[r] * rz[r];
             }
         } else {
+            // ---- joint polish step: one projection round of the primal point onto the
+            // active face and one least-squares refinement of the multipliers share the
+            // DMMA pass, the (half-warp split) solve and the G-multiplication ----
 #pragma unroll
             for (int r = 0; r < RPL; ++r) { rz[r] = 0.0; d[r] = 0.0; sinv[r] = 0.0; zinv[r] = 0.0; }
-            bool fallback = false;
-            if (round == 1 || round == 2) {
-                // the projection usually lands on the face after one or two rounds: skip the rest
-                double t = 0.0;
+            float ft = 0.f, fslack = -3.0e38f, fymin = -3.0e38f, fymax = 0.f;
 #pragma unroll
-                for (int r = 0; r < RPL; ++r)
-                    if (act[r]) t = fmax(t, fabs(h[r] - gx[r]));
-                t = warp_max(t);
-                if (PB_UNI(t <= 1e-13 * fmax(1.0, hmax))) round = 3;
-            }
-            if (round < 3) {
-                // projection rounds: residual of the active rows at the current point
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) w.V[lane + 32 * r] = act[r] ? h[r] - gx[r] : 0.0;
-            } else if (round == 3) {
-                // polished point: no row violated, active rows tight
-                double slack = 1e300, tight = 0.0;
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    if (live[r]) slack = fmin(slack, h[r] - gx[r]);
-                    if (act[r]) tight = fmax(tight, fabs(h[r] - gx[r]));
+            for (int r = 0; r < RPL; ++r) {
+                const double res_r = h[r] - gx[r];
+                if (act[r]) {
+                    y[r] -= gu[r];           // y -= G_B u,  u = (G_B'G_B)^-1 (G_B'y + c)  (u = 0 in round 0)
+                    ft = fmaxf(ft, __double2float_ru(fabs(res_r)));
+                    fymin = fmaxf(fymin, __double2float_ru(-y[r]));
+                    fymax = fmaxf(fymax, __double2float_ru(y[r]));
                 }
-                slack = warp_min(slack);
-                const bool feasible = slack >= -1e-9 * fmax(1.0, hmax);
-                if (PB_UNI(!early)) {
-                    // final polish of a tightly converged iterate: objective must agree
+                if (live[r]) fslack = fmaxf(fslack, __double2float_ru(-res_r));
+                w.V[0 * MP + lane + 32 * r] = act[r] ? res_r : 0.0;
+                w.V[1 * MP + lane + 32 * r] = y[r];
+            }
+            __syncwarp();
+            s_gt_times_slots<RPL>(w, mk, 2, lane);
+            float frd = own ? __double2float_ru(fabs(w.R[NS + lane] + cl0)) : 0.f;      // |G_B'y + c|
+            warp_max5f(ft, fslack, fymin, fymax, frd);
+            const double scale = fmax(1.0, hmax);
+            const bool feasible = (double)fslack <= 1e-9 * scale;
+            const bool settled = (double)ft <= 1e-13 * scale || round == 3;    // projection converged (or out of rounds)
+            if (PB_UNI(!early)) {
+                // final polish of a tightly converged iterate: objective must agree
+                if (PB_UNI(settled)) {
                     const double f1 = warp_sum(cl0 * xp);
                     if (PB_UNI(feasible && (fabs(f1 - f0) <= 1e-6 * fmax(1.0, fabs(f0))))) { res.x = xp; res.fun = f1; }
                     break;
                 }
-                tight = warp_max(tight);
-                if (PB_UNI(feasible && tight <= 1e-9 * fmax(1.0, hmax))) {
-                    // start the dual certificate: y = z / tau on the active rows
-                    const double te = 1.0 / tau;
-#pragma unroll
-                    for (int r = 0; r < RPL; ++r) {
-                        y[r] = act[r] ? z[r] * te : 0.0;
-                        w.V[lane + 32 * r] = y[r];
-                    }
-                } else {
-                    fallback = true;
-                }
             } else {
-                // certificate refinement: gx = G u with u = (G_B'G_B)^-1 (G_B'y + c)
-                ymin = 1e300; ymax = 0.0;
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    if (act[r]) { y[r] -= gx[r]; ymin = fmin(ymin, y[r]); ymax = fmax(ymax, y[r]); }
-                    w.V[lane + 32 * r] = y[r];
+                const bool dual_ok = (double)frd <= 1e-9 * sqrt(nc2) && (double)fymin <= 1e-9 * fmax(1.0, (double)fymax);
+                if (PB_UNI(settled && feasible && (double)ft <= 1e-9 * scale && dual_ok)) {
+                    // primal feasible, active rows tight, dual feasible, complementary: optimal
+                    res.status = ST_OPTIMAL;
+                    res.x = xp;
+                    res.fun = warp_sum(cl0 * xp);
+                    break;
                 }
-            }
-            if (PB_UNI(fallback)) {
-                // resume the interior-point iterations from the untouched iterate
-                phase = 0; early = false;
-                if (own) Xx[lane] = xl;
-                __syncwarp();
-                continue;
+                if (PB_UNI(round == 3)) {
+                    // not certified: resume the interior-point iterations from the untouched iterate
+                    phase = 0; early = false;
+                    if (own) { Xx[lane] = xl; X2[lane] = 0.0; }
+                    __syncwarp();
+                    continue;
+                }
             }
         }
-        __syncwarp();
-        s_gt_times_slots<RPL>(w, mk, phase == 0 ? 3 : 1, lane);
-        if (phase == 1 && round >= 4) {
-            // refined multipliers: dual feasible already?  (usually after the first refinement)
-            const double rd = own ? fabs(w.R[lane] + cl0) : 0.0;      // |G_B'y + c|
-            const double rdmax = warp_max(rd);
-            const double ylo = warp_min(ymin), yhi = warp_max(ymax);
-            if (PB_UNI(rdmax <= 1e-9 * sqrt(nc2) && ylo >= -1e-9 * fmax(1.0, yhi))) {
-                // primal feasible, dual feasible, complementary: optimal
-                res.status = ST_OPTIMAL;
-                res.x = xp;
-                res.fun = warp_sum(cl0 * xp);
-                break;
-            }
-            if (round == 5) {
-                // not certified: resume the interior-point iterations from the untouched iterate
-                phase = 0; early = false;
-                if (own) Xx[lane] = xl;
-                __syncwarp();
-                continue;
-            }
+        if (phase == 0) {
+            __syncwarp();
+            s_gt_times_slots<RPL>(w, mk, 3, lane);
         }
         const bool refactor = (phase == 0) || (round == 0);
         if (refactor) s_normal_matrix<RPL>(w, mk, lane);
@@ -524,8 +508,11 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                 }
                 if (nact > 0) {
 #pragma unroll
-                    for (int r = 0; r < RPL; ++r) w.d[lane + 32 * r] = act[r] ? 1.0 : 0.0;
-                    if (own) Xx[lane] = xp;
+                    for (int r = 0; r < RPL; ++r) {
+                        w.d[lane + 32 * r] = act[r] ? 1.0 : 0.0;
+                        y[r] = act[r] ? z[r] * te : 0.0;      // multipliers of the active rows
+                    }
+                    if (own) { Xx[lane] = xp; X2[lane] = 0.0; }
                     __syncwarp();
                     phase = 1; round = 0;
                     continue;
@@ -574,7 +561,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
         for (int pass = 0; pass < npass; ++pass) {
             if (own) {
                 double ra, rb = 0.0;
-                if (phase == 1) ra = round < 3 ? w.R[lane] : w.R[lane] + cl0;
+                if (phase == 1) { ra = w.R[lane]; rb = w.R[NS + lane] + cl0; }      // projection | refinement
                 else if (pass == 0) { ra = w.R[NS + lane] - cl; rb = w.R[2 * NS + lane] - rxl; }
                 else ra = fma(-eta, rxl, w.R[lane]);
                 X1[lane] = ra;
@@ -583,10 +570,7 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             __syncwarp();
             s_solve<2>(w.M, X1, lane);
             if (phase == 1) {
-                if (own) {
-                    if (round < 3) { xp += X1[lane]; Xx[lane] = xp; }
-                    else Xx[lane] = X1[lane];           // certificate: next step multiplies G by u
-                }
+                if (own) { xp += X1[lane]; Xx[lane] = xp; }      // X2 keeps u for the next step's G u
                 ++round;
                 __syncwarp();
                 break;
