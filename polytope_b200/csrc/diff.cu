@@ -457,6 +457,7 @@ int pb200_region_diff_batch(const double* PA, const double* Pb, const int32_t* p
                             int32_t* piece_reduce, int32_t* piece_owner, int32_t* piece_seq, long long piece_cap, int piece_m,
                             long long* pieces_used, int32_t* status, int32_t* n_pieces, int32_t* n_lp, int* work_counter,
                             void* stream) {
+    if (T == 0) return PB200_OK;
     if (T < 0 || !PA || !Pb || !RA || !Rb || !piece_A || !piece_b || !piece_rows || !piece_reduce || !piece_owner || !piece_seq ||
         !pieces_used || !status || !n_pieces || !n_lp || !work_counter)
         return fail(PB200_EINVAL, "pb200_region_diff_batch: null pointer or negative batch");

@@ -715,6 +715,7 @@ int pb200_hull_batch(const double* points, const int32_t* n_pts, int H, int Nmax
                      double* out_A, double* out_b, int32_t* out_vid, long long out_cap, long long* facet_off, int32_t* facet_cnt,
                      int32_t* status, uint8_t* is_vertex, int32_t* stats, long long* total_facets, void* workspace,
                      size_t workspace_bytes, void* stream) {
+    if (H == 0) return PB200_OK;
     if (H < 0 || !points || !out_A || !out_b || !out_vid || !facet_off || !facet_cnt || !status || !total_facets || !workspace)
         return fail(PB200_EINVAL, "pb200_hull_batch: null pointer or negative batch");
     if (d < 2 || d > HULL_MAX_D) return fail(PB200_EUNSUPPORTED, "hull: need 2 <= d <= 16");
@@ -759,6 +760,7 @@ int pb200_hull_batch(const double* points, const int32_t* n_pts, int H, int Nmax
 
 int pb200_dual_points(const double* A, const double* b, const int32_t* m_rows, const double* xc, int P, int m, int d,
                       double* out, void* stream) {
+    if (P == 0) return PB200_OK;
     if (P < 0 || !A || !b || !xc || !out) return fail(PB200_EINVAL, "pb200_dual_points: null pointer");
     if (P == 0) return PB200_OK;
     dual_points_kernel<<<blocks_for((long long)P * m, 256), 256, 0, (cudaStream_t)stream>>>(A, b, m_rows, xc, P, m, d, out);

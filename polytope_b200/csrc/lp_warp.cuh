@@ -44,7 +44,10 @@ constexpr int LP_MAX_N = 32;            // columns (n-vectors are lane-owned)
 constexpr double LP_FEAS_TOL = 1e-9;
 constexpr double LP_GAP_TOL = 1e-9;
 constexpr double LP_STEP = 0.99;
-constexpr double LP_EARLY_TOL = 1e-2;      // tolerance at which the certified polish is first tried
+#ifndef PB200_EARLY_TOL
+#define PB200_EARLY_TOL 1e-2
+#endif
+constexpr double LP_EARLY_TOL = PB200_EARLY_TOL;      // tolerance at which the certified polish is first tried
 constexpr double LP_EARLY_NEXT = 1e-2;     // a failed attempt is repeated once the residuals shrank by this factor
 constexpr int NSLOT = 4;                // vector slots of a G'V pass
 

@@ -668,6 +668,7 @@ long long pb200_launch_count(void) { return g_launches; }
 
 int pb200_lp_batch(const double* G, const double* h, const double* c, const int32_t* m_rows, int B, int m, int n,
                    double* x, double* fun, int8_t* status, int32_t* iters, void* stream) {
+    if (B == 0) return PB200_OK;
     if (B < 0 || !G || !h || !c || !x || !fun || !status) return fail(PB200_EINVAL, "pb200_lp_batch: null pointer or negative batch");
     GenericLP prob{G, h, c, m_rows, m, n, x, fun, status, iters};
     return launch_lp(prob, B, m, n, (cudaStream_t)stream);
@@ -675,6 +676,7 @@ int pb200_lp_batch(const double* G, const double* h, const double* c, const int3
 
 int pb200_normalize_batch(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, double* An,
                           double* bn, uint64_t* valid, void* stream) {
+    if (P == 0) return PB200_OK;
     if (P < 0 || !A || !b || !An || !bn) return fail(PB200_EINVAL, "pb200_normalize_batch: null pointer");
     if (m < 1 || m > 64 || d < 1 || d > 128) return fail(PB200_EUNSUPPORTED, "normalize: need 1<=m<=64, 1<=d<=128");
     if (P == 0) return PB200_OK;
@@ -686,6 +688,7 @@ int pb200_normalize_batch(const double* A, const double* b, const int32_t* m_row
 
 int pb200_cheby_batch(const double* A, const double* b, const int32_t* m_rows, const uint64_t* rows, int P, int m,
                       int d, double* r, double* xc, int8_t* status, void* stream) {
+    if (P == 0) return PB200_OK;
     if (P < 0 || !A || !b || !r || !xc || !status) return fail(PB200_EINVAL, "pb200_cheby_batch: null pointer");
     if (rows && m > 64) return fail(PB200_EUNSUPPORTED, "row masks need m <= 64");
     ChebyLP prob{A, b, m_rows, rows, nullptr, 0, m, d, r, xc, status, nullptr};
@@ -694,6 +697,7 @@ int pb200_cheby_batch(const double* A, const double* b, const int32_t* m_rows, c
 
 int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, double* lo,
                      double* hi, int8_t* status, void* stream) {
+    if (P == 0) return PB200_OK;
     if (P < 0 || !A || !b || !lo || !hi || !status) return fail(PB200_EINVAL, "pb200_bbox_batch: null pointer");
     if (d < 1 || d > LP_MAX_N) return fail(PB200_EUNSUPPORTED, "bbox: need 1 <= d <= 32");
     if (P == 0) return PB200_OK;
@@ -716,6 +720,7 @@ size_t pb200_reduce_workspace_bytes(int P, int m, int d) {
 int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, double abs_tol,
                        int normalize, uint64_t* keep, uint32_t* flags, double* r, double* xc, double* b_out, double* A_out,
                        int32_t* n_lp, int32_t* lp_iters, void* workspace, size_t workspace_bytes, void* stream) {
+    if (P == 0) return PB200_OK;
     if (P < 0 || !A || !b || !keep || !flags || !r || !xc || !b_out || !workspace)
         return fail(PB200_EINVAL, "pb200_reduce_batch: null pointer");
     if (m < 1 || m > 64) return fail(PB200_EUNSUPPORTED, "reduce: need 1 <= m <= 64 rows (row sets are 64-bit masks)");
@@ -788,6 +793,7 @@ int pb200_profile_read(float* stage_ms, int n) {
 int pb200_adjacent_pairs(const double* A, const double* b, int ncell, int mc, int d, const int32_t* pair_i,
                          const int32_t* pair_j, long long T, double abs_tol, uint8_t* adjacent, double* radius,
                          int8_t* status, void* stream) {
+    if (T == 0) return PB200_OK;
     if (!A || !b || !adjacent || T < 0 || ncell < 0) return fail(PB200_EINVAL, "pb200_adjacent_pairs: bad argument");
     if ((pair_i == nullptr) != (pair_j == nullptr)) return fail(PB200_EINVAL, "pair_i and pair_j must both be given or both NULL");
     if (!pair_i && T != (long long)ncell * (ncell - 1) / 2)

@@ -410,19 +410,20 @@ extern "C" {
 
 int pb200_contains_batch(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, const double* points,
                          long long N, double abs_tol, int any_of, uint8_t* out, void* stream) {
-    if (P < 0 || N < 0 || !A || !b || !points || !out) return fail(PB200_EINVAL, "pb200_contains_batch: null pointer or negative size");
-    if (d < 1 || d > 32) return fail(PB200_EUNSUPPORTED, "contains: need 1 <= d <= 32");
-    if (m < 1 || m * (d + 3) > CHUNK_DOUBLES) return fail(PB200_EUNSUPPORTED, "contains: need 1 <= m and m*(d+3) <= 4096");
     if (N == 0) return PB200_OK;
-    if (P == 0) {
+    if (P == 0 && out) {          // no polytopes: nothing contains anything
         if (any_of) PB_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)N, (cudaStream_t)stream));
         return PB200_OK;
     }
+    if (P < 0 || N < 0 || !A || !b || !points || !out) return fail(PB200_EINVAL, "pb200_contains_batch: null pointer or negative size");
+    if (d < 1 || d > 32) return fail(PB200_EUNSUPPORTED, "contains: need 1 <= d <= 32");
+    if (m < 1 || m * (d + 3) > CHUNK_DOUBLES) return fail(PB200_EUNSUPPORTED, "contains: need 1 <= m and m*(d+3) <= 4096");
     PB_DISPATCH_D(d, launch_contains, A, b, m_rows, P, m, d, points, N, abs_tol, any_of ? 1 : 0, out, (cudaStream_t)stream);
 }
 
 int pb200_volume_counts(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, const double* lo,
                         const double* hi, long long N, const uint64_t* rng_state, unsigned long long* count, void* stream) {
+    if (P == 0) return PB200_OK;
     if (P < 0 || N < 1 || !A || !b || !lo || !hi || !rng_state || !count)
         return fail(PB200_EINVAL, "pb200_volume_counts: null pointer, negative batch or nsamples < 1");
     if (d < 1 || d > 32) return fail(PB200_EUNSUPPORTED, "volume: need 1 <= d <= 32");
@@ -434,6 +435,7 @@ int pb200_volume_counts(const double* A, const double* b, const int32_t* m_rows,
 
 int pb200_point_facet_sweep(const double* points, const double* normals, const double* offsets, long long N, int F, int d,
                             double tol, int32_t* first_facet, int32_t* far_facet, double* far_dist, void* stream) {
+    if (N == 0) return PB200_OK;
     if (N < 0 || F < 0 || !points || !normals || !offsets) return fail(PB200_EINVAL, "pb200_point_facet_sweep: null pointer or negative size");
     if (d < 1 || d > 32) return fail(PB200_EUNSUPPORTED, "sweep: need 1 <= d <= 32");
     if (N == 0) return PB200_OK;

@@ -415,7 +415,7 @@ def hull_batch(points, n_pts=None, abs_tol=ABS_TOL, facet_cap=None, out_cap=None
         status = torch.empty(H, dtype=torch.int32, device='cuda')
         isv = torch.empty((H, nmax), dtype=torch.uint8, device='cuda')
         stats = torch.empty((H, 2), dtype=torch.int32, device='cuda')
-        total = torch.empty(1, dtype=torch.int64, device='cuda')
+        total = torch.zeros(1, dtype=torch.int64, device='cuda')
         _capi.check(lib.pb200_hull_batch(pts.data_ptr(), npt_ptr, H, nmax, d, float(abs_tol), cap, A.data_ptr(),
                                          b.data_ptr(), vid.data_ptr(), pool, off.data_ptr(), cnt.data_ptr(),
                                          status.data_ptr(), isv.data_ptr(), stats.data_ptr(), total.data_ptr(),
@@ -515,7 +515,7 @@ def region_diff_batch(PA, Pb, RA, Rb, p_rows=None, r_rows=None, n_reg=None, abs_
     status = torch.empty(T, dtype=torch.int32, device='cuda')
     npieces = torch.empty(T, dtype=torch.int32, device='cuda')
     nlp = torch.empty(T, dtype=torch.int32, device='cuda')
-    used = torch.empty(1, dtype=torch.int64, device='cuda')
+    used = torch.zeros(1, dtype=torch.int64, device='cuda')
     counter = torch.empty(1, dtype=torch.int32, device='cuda')
     for _ in range(max_tries):
         pA = torch.empty((cap, piece_m, d), dtype=torch.float64, device='cuda')

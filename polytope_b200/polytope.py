@@ -966,6 +966,30 @@ def region_diff_batch(polys, regs, abs_tol=ABS_TOL, intersect_tol=ABS_TOL):
             cells_of.append(reg.list_poly)
     if not todo:
         return out
+    # Regions beyond the kernel's per-problem envelope (64 cells, 2048 cell rows): only the
+    # cells that intersect the minuend take part in the search (polytope.py:2146-2157), so
+    # find those first with one batch of Chebyshev LPs and hand the kernel the survivors
+    # (original order kept: the kernel's stable sort by radius then matches the reference's).
+    if any(len(c) > 64 or sum(p.A.shape[0] for p in c) > 2048 for c in cells_of):
+        tests, where = [], []
+        for t, k in enumerate(todo):
+            for i, cell in enumerate(cells_of[t]):
+                tests.append(Polytope(np.vstack([polys[k].A, cell.A]), np.hstack([polys[k].b, cell.b])))
+                where.append((t, i))
+        hit = [[] for _ in todo]
+        for (t, i), (rc, _) in zip(where, cheby_ball_batch(tests)):
+            if rc >= intersect_tol:
+                hit[t].append(cells_of[t][i])
+        keep_t = []
+        for t, k in enumerate(todo):
+            if hit[t]:
+                keep_t.append(t)
+            else:
+                out[k] = polys[k].copy()       # no cell intersects poly: the reference returns poly
+        todo = [todo[t] for t in keep_t]
+        cells_of = [hit[t] for t in keep_t]
+        if not todo:
+            return out
     PA, Pb, prow = _stack([polys[k] for k in todo])
     shared = all(c is cells_of[0] for c in cells_of)
     groups = [cells_of[0]] if shared else cells_of

@@ -115,3 +115,36 @@ def test_region_diff_batch_vs_oracle(d, m, ncell, T):
             assert np.array_equal(res.A[o + k][:len(b)], A) and np.array_equal(res.b[o + k][:len(b)], b)
         n_checked += 1
     assert n_checked > 0
+
+
+def test_region_diff_with_many_cells_prefilters_on_the_host():
+    """A region of 15 x 15 = 225 unit cells (beyond the kernel's 64 cells per problem): only the
+    cells meeting the minuend reach the device search; results equal the oracle's."""
+    import polytope_b200 as pc
+    from oracle import polytope_oracle as orc
+    cells = [pc.box2poly([[i, i + 1], [j, j + 1]]) for i in range(15) for j in range(15)]
+    reg = pc.Region(cells)
+    for iv in ([[2.5, 4.25], [3.5, 4.5]], [[-3, -2], [0, 1]], [[0.2, 0.8], [0.3, 0.6]], [[13.5, 16], [13.5, 15.5]]):
+        poly = pc.box2poly(iv)
+        got = pc.region_diff(poly, reg)
+        kind, pieces = orc.region_diff((poly.A, poly.b), [(c.A, c.b) for c in cells])
+        if kind == 'poly':
+            assert len(got) == 0 and np.array_equal(got.A, poly.A)
+            continue
+        want = []
+        for A, b, reduced in pieces:
+            if reduced:
+                red = orc.reduce(A, b)
+                if red['empty']:
+                    continue
+                want.append(orc.normalize_rows(red['A'], red['b'])[:2])
+            else:
+                want.append(orc.normalize_rows(A, b)[:2])
+        have = pieces_of(got)
+        assert len(have) == len(want)
+        for (A1, b1), (A2, b2) in zip(have, want):
+            np.testing.assert_allclose(A1, A2, atol=1e-9)
+            np.testing.assert_allclose(b1, b2, atol=1e-9)
+    # is_subset against the big region goes through the same path
+    assert pc.is_subset(pc.box2poly([[1.5, 3.5], [2.5, 3.5]]), reg)
+    assert not pc.is_subset(pc.box2poly([[14.5, 15.5], [2.5, 3.5]]), reg)

@@ -109,3 +109,16 @@ def test_extreme_vs_oracle_at_baseline_sizes(m, d, n):
         slack = polys[i].b[None, :] - Vs[i] @ polys[i].A.T
         assert slack.min() > -1e-7
         assert ((np.abs(slack) < 1e-7).sum(1) >= d).all()
+
+
+def test_empty_batches_are_fine():
+    import torch
+    from polytope_b200 import engine
+    res = engine.hull_batch(np.zeros((0, 5, 3)))
+    assert len(res.status) == 0 and len(res.b) == 0
+    d = engine.region_diff_batch(np.zeros((0, 4, 2)), np.zeros((0, 4)), np.zeros((1, 4, 2)), np.zeros((1, 4)))
+    assert len(d.status) == 0 and len(d.rows) == 0
+    assert engine.contains_batch(np.zeros((1, 2, 2)), np.zeros((1, 2)), np.zeros((2, 0))).shape == (1, 0)
+    r = engine.reduce_batch(torch.zeros((0, 4, 2), dtype=torch.float64, device='cuda'),
+                            torch.zeros((0, 4), dtype=torch.float64, device='cuda'))
+    assert len(r.keep) == 0
