@@ -188,12 +188,17 @@ __device__ __forceinline__ void block_compact_range(BlockScratch& bs, int n, int
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int c0 = 0; c0 < n; c0 += HT * Q) {
         unsigned masks[Q];
+        bool fl[Q];
         int mine = 0;
+        // all eight evaluations first (their loads overlap), then the eight ballots
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int f = c0 + wid * (32 * Q) + 32 * q + lane;
-            const bool fl = f < n && flag(f);
-            masks[q] = __ballot_sync(FULL, fl);
+            fl[q] = f < n && flag(f);
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            masks[q] = __ballot_sync(FULL, fl[q]);
             mine += __popc(masks[q]);
         }
         if (lane == 0) bs.cnt[parity][wid] = mine;
@@ -241,6 +246,15 @@ constexpr uint32_t DUP_BIT = 0x80000000u;
 // Lane r (< D) of the group holds vertex id `myv` (sorted ascending over r).
 // Solves V x = 1 by Gauss-Jordan with row pivoting; n = x / |x|, off = 1 / |x|
 // (quickhull.py:66-85 solves the same system bordered by one row/column).
+// reciprocal: MUFU seed + two Newton steps (<= 1-2 ulp); the IEEE division sequence is ~3x longer
+__device__ __forceinline__ double hull_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
 template <int D>
 __device__ __forceinline__ bool facet_plane(const double* __restrict__ X, int ldx, int myv, int gl, double (&nk)[1], int& mycol,
                                             double& off) {
@@ -263,7 +277,7 @@ __device__ __forceinline__ bool facet_plane(const double* __restrict__ X, int ld
         if (best < 32u) ok = false;                       // every candidate was (sub)zero
         const int who = (int)((best - 16u) & 0xfu);
         const double pv = __shfl_sync(FULL, a[k], who, 16);
-        const double rinv = 1.0 / pv;
+        const double rinv = hull_rcp(pv);
         const double f = (gl == who) ? 0.0 : a[k] * rinv;
 #pragma unroll
         for (int j = k + 1; j <= D; ++j) {
@@ -277,14 +291,15 @@ __device__ __forceinline__ bool facet_plane(const double* __restrict__ X, int ld
 #pragma unroll
     for (int k = 0; k < D; ++k)
         if (mycol == k) piv = a[k];
-    const double xk = mycol >= 0 ? a[D] / piv : 0.0;
+    const double xk = mycol >= 0 ? a[D] * hull_rcp(piv) : 0.0;
     double s = xk * xk;
 #pragma unroll
     for (int o = 8; o; o >>= 1) s += __shfl_xor_sync(FULL, s, o, 16);
     const double mult = sqrt(s);
     if (!(mult > 0.0) || !(mult < 1e300)) ok = false;
-    nk[0] = xk / mult;
-    off = 1.0 / mult;
+    const double minv = hull_rcp(mult);
+    nk[0] = xk * minv;
+    off = minv;
     return ok;
 }
 
@@ -473,7 +488,9 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         int nV = 0;
         block_compact_range(bs, hi, nV, parity,
                             [&](int f) {
-                                const bool v = w.state[f] == 1 && facet_dist(w, cap, d, f, p) > a.tol;
+                                // distance first, liveness second: no control dependence between the loads
+                                const double dist = facet_dist(w, cap, d, f, p);
+                                const bool v = (dist > a.tol) & (w.state[f] == 1);
                                 w.vis[f] = v ? 1 : 0;
                                 return v;
                             },
