@@ -313,7 +313,9 @@ __device__ __forceinline__ bool make_facets(const HullWs& w, int cap, int ldx, i
     for (int rnd = 0; rnd < rounds; ++rnd) {
         const int k = rnd * NG + group;
         const bool act = k < count;
-        const int myv = (act && gl < D) ? get_id(k, gl) : 0;
+        // get_id may use half-warp collectives: every lane calls it (idle groups redo the last item)
+        const int v = get_id(act ? k : count - 1, gl);
+        const int myv = (act && gl < D) ? v : 0;
         double nk[1];
         int mycol;
         double off;
@@ -551,11 +553,14 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         ok = make_facets<D>(w, cap, ldx, nH, [&](int k, int gl) {
             const int item = w.hor_list[k];
             const int f = item / d, i = item - f * d;
-            // position of pstar in the sorted ridge
-            int pos = 0;
-            for (int t = 0; t < d - 1; ++t) pos += ridge_elem(w.vid, cap, f, i, t) < pstar ? 1 : 0;
-            if (gl == pos) return pstar;
-            return ridge_elem(w.vid, cap, f, i, gl < pos ? gl : gl - 1);
+            // lane t < d-1 of the half warp fetches element t of the sorted ridge; pstar is
+            // merged in at its sorted position with one ballot and one shuffle
+            const int e = gl < d - 1 ? ridge_elem(w.vid, cap, f, i, gl) : 0x7fffffff;
+            const unsigned less = __ballot_sync(FULL, e < pstar);
+            const int pos = __popc((less >> (threadIdx.x & 16)) & 0xffffu);
+            const int src = gl < pos ? gl : gl - 1;
+            const int other = __shfl_sync(FULL, e, src < 0 ? 0 : src, 16);
+            return gl == pos ? pstar : other;
         }) && ok;
         __syncthreads();
         // (f) orphaned outside points go to the first new facet (in cone order) they are
