@@ -266,14 +266,17 @@ __device__ __forceinline__ bool facet_plane(const double* __restrict__ X, int ld
     bool used = !row;
     mycol = -1;
     bool ok = true;
-    const unsigned half_mask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         // row pivot: largest |a[k]| among the unused rows of this half warp.  The magnitude
         // (as fp32 bits, order-preserving for non-negative floats) and the lane share one
-        // 32-bit key, so the search is a single warp reduction; ties go to the higher lane.
+        // 32-bit key, so the search is one 4-step integer butterfly; ties go to the higher lane.
         const unsigned key = used ? 0u : ((__float_as_uint(__double2float_rd(fabs(a[k]))) & ~0xfu) | (unsigned)gl) + 16u;
-        const unsigned best = __reduce_max_sync(half_mask, key);
+        // butterfly over the 16 lanes of the half warp (a redux with two different member masks
+        // compiles to WARPSYNC.EXCLUSIVE: the two halves would run one after the other)
+        unsigned best = key;
+#pragma unroll
+        for (int o = 8; o; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o, 16));
         if (best < 32u) ok = false;                       // every candidate was (sub)zero
         const int who = (int)((best - 16u) & 0xfu);
         const double pv = __shfl_sync(FULL, a[k], who, 16);
