@@ -629,17 +629,19 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
     __syncthreads();
     const long long o = *reinterpret_cast<volatile long long*>(sh_flag);
     if (o + nF > a.out_cap) { finish(HS_OUT_CAP, nF, o, inserted, created); return; }
+    // row-major outputs written element-wise: consecutive threads write consecutive addresses
+    for (long long e = tid; e < (long long)nF * d; e += HT) {
+        const int k = (int)(e / d), c = (int)(e - (long long)k * d);
+        const int f = w.vis_list[k];
+        a.outA[(size_t)o * d + e] = w.nrm[(size_t)c * cap + f];
+        const int v = w.vid[(size_t)c * cap + f];
+        a.outV[(size_t)o * d + e] = v;
+        if (a.is_vertex) a.is_vertex[(size_t)h * Nmax + v] = 1;
+    }
     for (int k = tid; k < nF; k += HT) {
         const int f = w.vis_list[k];
         double dot = 0.0;
-        for (int c = 0; c < d; ++c) {
-            const double nc = w.nrm[(size_t)c * cap + f];
-            a.outA[(size_t)(o + k) * d + c] = nc;
-            dot = fma(nc, sh_c[c], dot);
-            const int v = w.vid[(size_t)c * cap + f];
-            a.outV[(size_t)(o + k) * d + c] = v;
-            if (a.is_vertex) a.is_vertex[(size_t)h * Nmax + v] = 1;
-        }
+        for (int c = 0; c < d; ++c) dot = fma(w.nrm[(size_t)c * cap + f], sh_c[c], dot);
         a.outb[o + k] = w.off[f] + dot;
     }
     finish(HS_OK, nF, o, inserted, created);
