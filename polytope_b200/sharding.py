@@ -84,3 +84,48 @@ def adjacency_sharded(A, b, group=None, abs_tol=1e-7):
         adj, _, _ = engine.adjacent_pairs(Ad, bd, pi, pj, abs_tol=abs_tol)
         return (adj,)
     return sharded_map(local, T, group)[0]
+
+
+def allgather_ragged(rows, group=None):
+    """Concatenate every rank's `rows` (first dimension of any length) in rank order:
+    the row counts are all-gathered first, then one padded all_gather moves the data
+    (variable-length outputs such as extreme()'s vertices).
+    -> (all_rows, counts int64[world])"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return rows, torch.tensor([rows.shape[0]], dtype=torch.int64)
+    world = dist.get_world_size(group)
+    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    counts = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = torch.cat(counts).cpu()
+    big = int(counts.max())
+    pad = rows.new_zeros((big,) + tuple(rows.shape[1:]))
+    pad[:rows.shape[0]] = rows
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([o[:int(c)] for o, c in zip(out, counts)], 0), counts
+
+
+def extreme_sharded(polys, group=None, gather_vertices=True):
+    """cfg4: extreme() of a list of polytopes, the list split across the ranks of `group`
+    (contiguous blocks).  Every rank enumerates the vertices of its own block on its GPU;
+    the per-polytope vertex counts are all-gathered, and (optionally) the vertices
+    themselves with one padded all-gather.
+    -> (counts int64[P] on every rank, vertices [sum(counts), d] or this rank's own rows)"""
+    from polytope_b200 import polytope as pc
+    import numpy as np
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    lo, hi = shard_bounds(len(polys), rank, world)
+    local = pc.extreme_batch(polys[lo:hi])
+    d = polys[0].dim
+    cnt = torch.tensor([0 if v is None else len(v) for v in local], dtype=torch.int64, device='cuda')
+    V = np.concatenate([v for v in local if v is not None] or [np.zeros((0, d))], 0)
+    Vt = torch.from_numpy(np.ascontiguousarray(V)).to('cuda')
+    if world == 1:
+        return cnt, Vt
+    counts = allgather_blocks(cnt, len(polys), group)
+    if not gather_vertices:
+        return counts, Vt
+    allV, _ = allgather_ragged(Vt, group)
+    return counts, allV

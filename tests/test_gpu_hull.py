@@ -122,3 +122,13 @@ def test_empty_batches_are_fine():
     r = engine.reduce_batch(torch.zeros((0, 4, 2), dtype=torch.float64, device='cuda'),
                             torch.zeros((0, 4), dtype=torch.float64, device='cuda'))
     assert len(r.keep) == 0
+
+
+def test_extreme_sharded_single_rank_equals_batch():
+    import polytope_b200 as pc
+    from polytope_b200 import sharding
+    polys = [pc.Polytope(*wl.box_cuts(8500 + 10 * 4 + i, 12, 4, True)) for i in range(3)]
+    counts, V = sharding.extreme_sharded(polys)
+    ref = pc.extreme_batch([pc.Polytope(p.A, p.b) for p in polys])
+    assert counts.tolist() == [len(v) for v in ref]
+    assert np.array_equal(V.cpu().numpy(), np.concatenate(ref, 0))

@@ -45,6 +45,12 @@ def _worker(rank, world, port, n_items, q):
             idx = torch.arange(lo, hi, dtype=torch.int64)
             return idx * idx + 1, (idx % 5).to(torch.int32), torch.stack([idx, -idx], 1).double()
         keep, flags, extra = sharding.sharded_map(fn, n_items)
+        # ragged gather (extreme()'s vertices): rank r contributes r + 2 rows
+        rows = torch.full((rank + 2, 3), float(rank))
+        allrows, counts = sharding.allgather_ragged(rows)
+        assert counts.tolist() == [r + 2 for r in range(world)]
+        assert allrows.shape == (sum(r + 2 for r in range(world)), 3)
+        assert torch.equal(allrows[:2], torch.zeros(2, 3)) and torch.equal(allrows[2:5], torch.ones(3, 3))
         q.put((rank, keep.numpy(), flags.numpy(), extra.numpy()))
     finally:
         dist.destroy_process_group()
