@@ -139,3 +139,11 @@ def test_ipm_model_matches_scipy_on_golden_lps(golden):
             assert abs(r['fun'] - g['fun'][i]) <= 1e-9 * (1 + abs(g['fun'][i]))
     r = ipm_model.solve_lp(np.array([1.]), np.array([[-1.]]), np.array([1.]))
     assert r['x'][0] == -1.0
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header must compile as C (and as C++) on its own."""
+    import subprocess
+    hdr = os.path.join(REPO, 'include', 'polytope_b200.h')
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c', hdr])
+    subprocess.check_call(['g++', '-std=c++11', '-Wall', '-Werror', '-fsyntax-only', '-x', 'c++', hdr])
