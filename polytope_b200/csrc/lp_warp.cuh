@@ -72,6 +72,25 @@ __device__ PB200_REDUCE_INLINE double warp_min(double v) {
     for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, o));
     return v;
 }
+// reciprocal / reciprocal square root: MUFU seed + two Newton steps (<= 1-2 ulp);
+// the IEEE-exact sequences cost ~20-30 instructions each and the r01 profile
+// showed them at ~12 % of all issue slots.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double p) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+    const double hp = 0.5 * p;
+    y = y * fma(-hp * y, y, 1.5);
+    y = y * fma(-hp * y, y, 1.5);
+    return y;
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -187,10 +206,10 @@ __device__ __forceinline__ unsigned cholesky(const WarpScratch& w, int n, int la
     for (int k = 0; k < n; ++k) {
         const double p = w.M[k * L + k];
         const double p0 = __shfl_sync(FULL_MASK, dg, k);
-        const bool ok = (p > 1e-13 * p0) && (p > 1e-30 * dmax) && (p < 1e300);
+        const bool ok = (p > 1e-13 * p0) && (p > 1e-30 * dmax) && (p > 1e-290) && (p < 1e300);
         double lik = 0.0;
         if (ok) {
-            const double rinv = 1.0 / sqrt(p);
+            const double rinv = fast_rsqrt(p);
             if (lane > k && lane < n) {
                 lik = w.M[lane * L + k] * rinv;
                 w.M[lane * L + k] = lik;
@@ -405,8 +424,8 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             const int i = lane + 32 * r;
-            sinv[r] = 1.0 / s[r];
-            zinv[r] = live[r] ? 1.0 / z[r] : 0.0;
+            sinv[r] = fast_rcp(s[r]);
+            zinv[r] = live[r] ? fast_rcp(z[r]) : 0.0;
             d[r] = z[r] * sinv[r];
             rz[r] = live[r] ? gx[0][r] + s[r] - h[r] * tau : 0.0;
             const double gxs = live[r] ? gx[0][r] + s[r] : 0.0;
@@ -431,10 +450,11 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
         const double rt = cx + hz + kap;
         const double mu = (sz + tau * kap) / (double)(mlive + 1);
         // ---- termination (cvxopt conelp-style tests) ----
-        const double pres = sqrt(rz2) / tau / nh;
-        const double dres = sqrt(rx2) / tau / nc;
-        const double pcost = cx / tau, dcost = -hz / tau;
-        const double gap = sz / (tau * tau);
+        const double tinv = fast_rcp(tau);
+        const double pres = sqrt(rz2) * tinv / nh;
+        const double dres = sqrt(rx2) * tinv / nc;
+        const double pcost = cx * tinv, dcost = -hz * tinv;
+        const double gap = sz * tinv * tinv;
         double relgap = 1e300;
         if (pcost < 0.0) relgap = gap / -pcost;
         else if (dcost > 0.0) relgap = gap / dcost;
@@ -522,10 +542,11 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
         hz1 = warp_sum(hz1); hz2 = warp_sum(hz2);
         const double cx1 = warp_sum(c * x1);
         double cx2 = warp_sum(c * sol[1]);
-        const double den = cx1 + hz1 - kap / tau;             // < 0
-        const double dta = (-rt + kap - cx2 - hz2) / den;
-        const double dka = -kap - kap * dta / tau;
-        double ratio = fmax(-dta / tau, -dka / kap);
+        const double den = cx1 + hz1 - kap * tinv;             // < 0
+        const double rden = fast_rcp(den), kinv = fast_rcp(kap);
+        const double dta = (-rt + kap - cx2 - hz2) * rden;
+        const double dka = -kap - kap * dta * tinv;
+        double ratio = fmax(-dta * tinv, -dka * kinv);
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {
             dza[r] = fma(dta, z1[r], dza[r]);
@@ -563,10 +584,10 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
         hz2 = warp_sum(hz2);
         cx2 = warp_sum(c * solc[0]);
         const double bk = -tau * kap + sigma * mu - dta * dka;
-        const double dtau = (-eta * rt - bk / tau - cx2 - hz2) / den;
-        const double dkap = (bk - kap * dtau) / tau;
+        const double dtau = (-eta * rt - bk * tinv - cx2 - hz2) * rden;
+        const double dkap = (bk - kap * dtau) * tinv;
         const double dx = solc[0] + dtau * x1;
-        ratio = fmax(-dtau / tau, -dkap / kap);
+        ratio = fmax(-dtau * tinv, -dkap * kinv);
         double ds[RPL];
 #pragma unroll
         for (int r = 0; r < RPL; ++r) {

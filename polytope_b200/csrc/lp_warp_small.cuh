@@ -49,25 +49,6 @@ __device__ inline SmallScratch lps_carve(double* base, int rpl) {
     return w;
 }
 
-// reciprocal / reciprocal square root: MUFU seed + two Newton steps (<= 1-2 ulp);
-// the IEEE-exact sequences cost ~20-30 instructions each and the r01 profile
-// showed them at ~12 % of all issue slots.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
-}
-__device__ __forceinline__ double fast_rsqrt(double p) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
-    const double hp = 0.5 * p;
-    y = y * fma(-hp * y, y, 1.5);
-    y = y * fma(-hp * y, y, 1.5);
-    return y;
-}
-
 __device__ PB200_REDUCE_INLINE void warp_sum3(double& a, double& b, double& c) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
