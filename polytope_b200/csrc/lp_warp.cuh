@@ -159,10 +159,15 @@ __device__ __forceinline__ void gt_times_slots(const WarpScratch& w, int mk, int
         const bool ca = col < n, cb = q < nslots;
         const double* ga = w.G + col * w.MP + t;
         const double* vb = w.V + q * w.MP + t;
-        for (int i0 = 0; i0 < mk; i0 += 4) {
-            const double a = ca ? ga[i0] : 0.0;
-            const double b = cb ? vb[i0] : 0.0;
-            dmma884(c0, c1, a, b);
+        // whole 32-row blocks (rows >= m are zero in G, V and d): the inner 8 steps unroll
+        for (int b0 = 0; b0 < mk; b0 += 32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i0 = b0 + 4 * u;
+                const double a = ca ? ga[i0] : 0.0;
+                const double b = cb ? vb[i0] : 0.0;
+                dmma884(c0, c1, a, b);
+            }
         }
         if (2 * t < NSLOT) {
             w.R[(2 * t) * w.NP + col] = c0;
@@ -183,10 +188,14 @@ __device__ __forceinline__ void form_normal_matrix(const WarpScratch& w, int mk,
             const double* gj = w.G + cj * w.MP + t;
             const double* gk = w.G + ck * w.MP + t;
             const double* dd = w.d + t;
-            for (int i0 = 0; i0 < mk; i0 += 4) {
-                const double a = bj ? gj[i0] * dd[i0] : 0.0;
-                const double b = bk ? gk[i0] : 0.0;
-                dmma884(c0, c1, a, b);
+            for (int b0 = 0; b0 < mk; b0 += 32) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i0 = b0 + 4 * u;
+                    const double a = bj ? gj[i0] * dd[i0] : 0.0;
+                    const double b = bk ? gk[i0] : 0.0;
+                    dmma884(c0, c1, a, b);
+                }
             }
             double* dst = w.M + cj * w.LDM + 8 * K + 2 * t;
             dst[0] = c0;
