@@ -122,7 +122,7 @@ struct Solver<RPL, false> {
 // cheby_ball(Polytope(A[idx], B[idx]))[0] for idx = list[0..cnt) followed by the
 // `extra_cnt` consecutive table rows extra0.. ; -1 signals an index error.
 template <int RPL, bool SMALL>
-__device__ double cheby_of_rows(const typename Solver<RPL, SMALL>::Scratch& w, const DiffState& s, const DiffProblem& q,
+__device__ __noinline__ double cheby_of_rows(const typename Solver<RPL, SMALL>::Scratch& w, const DiffState& s, const DiffProblem& q,
                                 const int* list, int cnt, int extra0, int extra_cnt, int lane, int& n_lp, bool& index_error) {
     const int d = q.d, total = cnt + extra_cnt;
     if (total > 32 * RPL) { index_error = true; return 0.0; }      // outside the kernel envelope
