@@ -245,6 +245,15 @@ int pb200_region_diff_batch(const double* PA, const double* Pb, const int32_t* p
 void pb200_profile_enable(int on);
 int pb200_profile_read(float* stage_ms, int n);
 
+/* Diagnostics: which kernel variant pb200_normalize_batch / pb200_reduce_batch
+ * use for the constructor normalisation (the batched (A|b) read).  -2 (default):
+ * tiled streaming kernel, bulk async copies (TMA) when the buffers are 16-byte
+ * aligned and m is even, 64-bit loads otherwise; 0 / 1 / 2 force 64-bit loads /
+ * 128-bit loads / bulk copies (still degrading to 64-bit when unaligned);
+ * -1 = row-per-lane kernel without shared-memory staging.  All variants produce
+ * identical bits; tools/normalize_bench.py measures them. */
+void pb200_normalize_variant(int variant);
+
 /* Number of kernels this library has launched since load (bench.py's
  * `gpu_launches` evidence). */
 long long pb200_launch_count(void);

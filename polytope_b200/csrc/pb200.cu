@@ -23,6 +23,7 @@
 #include "lp_warp.cuh"
 #include "lp_warp_small.cuh"
 #include "staging.cuh"
+#include "normalize.cuh"
 
 namespace pb200 {
 
@@ -439,6 +440,37 @@ __global__ void normalize_kernel(const double* __restrict__ A, const double* __r
     if (lane == 0 && valid) valid[p] = mask;
 }
 
+// Launch of the constructor normalisation.  Default: the tiled streaming kernel
+// (normalize.cuh) with bulk async copies when the spans are 16-byte aligned,
+// 64-bit coalesced loads otherwise.  pb200_normalize_variant() forces a variant
+// for A/B measurements (tools/normalize_bench.py): -1 = the row-per-lane kernel
+// above, 0 / 1 / 2 = 64-bit LDG / 128-bit LDG / bulk copies.
+static int g_norm_variant = -2;
+
+static int launch_normalize(const double* A, const double* b, const int32_t* m_rows, int P, int m, int d, int do_norm,
+                            double* An, double* bn, uint64_t* valid, cudaStream_t st) {
+    if (g_norm_variant == -1) {
+        normalize_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(A, b, m_rows, P, m, d, do_norm, An, bn, valid);
+        ++g_launches;
+        PB_CHECK_CUDA(cudaGetLastError());
+        return PB200_OK;
+    }
+    const bool aligned = (((uintptr_t)A | (uintptr_t)b | (uintptr_t)An | (uintptr_t)bn) & 15u) == 0 && (m & 1) == 0;
+    int mode = g_norm_variant == -2 ? NORM_BULK : g_norm_variant;
+    if (!aligned) mode = NORM_LDG64;
+    int nw = 8;                             // polytopes (warps) per CTA: two CTAs per SM must fit
+    while (nw > 1 && normalize_smem_doubles(nw, m, d) * sizeof(double) > 110 * 1024) nw >>= 1;
+    const size_t smem = normalize_smem_doubles(nw, m, d) * sizeof(double);
+    auto kern = mode == NORM_BULK ? normalize_tile_kernel<NORM_BULK>
+                : mode == NORM_LDG128 ? normalize_tile_kernel<NORM_LDG128> : normalize_tile_kernel<NORM_LDG64>;
+    if (smem > 48 * 1024) PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t div_magic = (1u << 20) / (uint32_t)d + 1u;
+    kern<<<blocks_for(P, nw), 32 * nw, smem, st>>>(A, b, m_rows, P, m, d, do_norm, div_magic, An, bn, valid);
+    ++g_launches;
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+
 // reduce(): is_fulldim verdict, b == inf drop and duplicate-direction filter
 // (polytope.py:1081-1116).  One warp per polytope.
 __global__ void prefilter_kernel(const double* __restrict__ An, const double* __restrict__ bn,
@@ -680,11 +712,10 @@ int pb200_normalize_batch(const double* A, const double* b, const int32_t* m_row
     if (P < 0 || !A || !b || !An || !bn) return fail(PB200_EINVAL, "pb200_normalize_batch: null pointer");
     if (m < 1 || m > 64 || d < 1 || d > 128) return fail(PB200_EUNSUPPORTED, "normalize: need 1<=m<=64, 1<=d<=128");
     if (P == 0) return PB200_OK;
-    normalize_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, (cudaStream_t)stream>>>(A, b, m_rows, P, m, d, 1, An, bn, valid);
-    ++g_launches;
-    PB_CHECK_CUDA(cudaGetLastError());
-    return PB200_OK;
+    return launch_normalize(A, b, m_rows, P, m, d, 1, An, bn, valid, (cudaStream_t)stream);
 }
+
+void pb200_normalize_variant(int variant) { g_norm_variant = variant < -2 || variant > 2 ? -2 : variant; }
 
 int pb200_cheby_batch(const double* A, const double* b, const int32_t* m_rows, const uint64_t* rows, int P, int m,
                       int d, double* r, double* xc, int8_t* status, void* stream) {
@@ -734,10 +765,8 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     if (lp_iters) PB_CHECK_CUDA(cudaMemsetAsync(lp_iters, 0, sizeof(int32_t) * P, st));
     stage_mark(0, st);
     // 1. constructor normalisation
-    normalize_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(A, b, m_rows, P, m, d, normalize ? 1 : 0, An, ws.bn,
-                                                                       ws.valid);
-    ++g_launches;
-    PB_CHECK_CUDA(cudaGetLastError());
+    rc = launch_normalize(A, b, m_rows, P, m, d, normalize ? 1 : 0, An, ws.bn, ws.valid, st);
+    if (rc) return rc;
     stage_mark(1, st);
     // 2. is_fulldim: one Chebyshev LP per polytope
     ChebyLP cheb{An, ws.bn, nullptr, ws.valid, nullptr, 0, m, d, r, xc, ws.cheb_status, lp_iters};

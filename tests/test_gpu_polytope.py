@@ -36,6 +36,39 @@ def test_normalize_is_bit_exact_with_numpy():
             assert np.array_equal(bn[p][pos], br), d
 
 
+@pytest.mark.parametrize('P,m,d', [(37, 33, 5), (37, 20, 8), (13, 64, 128), (1001, 32, 8), (5, 1, 4), (29, 64, 12)])
+def test_normalize_tiles_ragged_rows_and_variants(P, m, d):
+    """The tiled streaming kernel (bulk async copies when 16-byte aligned and m even, plain loads
+    otherwise): partial tiles, odd shapes, ragged m_rows -- against numpy via the oracle, and every
+    kernel variant against the default one bit for bit."""
+    from polytope_b200 import engine, _capi
+    from oracle import polytope_oracle as orc
+    rng = np.random.default_rng(P * 1000 + m * 10 + d)
+    A = rng.standard_normal((P, m, d)) * 10 ** rng.uniform(-3, 3, (P, m, 1))
+    b = rng.standard_normal((P, m))
+    A[P // 2, m // 2] = 0.0
+    mr = rng.integers(0, m + 1, P).astype(np.int32)
+    mr[0] = m
+    lib = _capi.lib()
+    try:
+        An, bn, valid = engine.normalize_batch(A, b, mr)
+        for p in range(P):
+            k = int(mr[p])
+            Ar, br, pos = orc.normalize_rows(A[p, :k], b[p, :k]) if k else (np.zeros((0, d)), np.zeros(0), [])
+            assert int(valid[p]) & (2 ** 64 - 1) == sum(1 << int(i) for i in pos)
+            assert np.array_equal(An[p][pos], Ar) and np.array_equal(bn[p][pos], br)
+            assert not An[p, k:].any() and not bn[p, k:].any()      # rows beyond m_rows come back as zeros
+        full = engine.normalize_batch(A, b)
+        for variant in (-1, 0, 1, 2):
+            lib.pb200_normalize_variant(variant)
+            for want, got in zip((An, bn, valid), engine.normalize_batch(A, b, mr)):
+                assert np.array_equal(want.view(np.uint64), got.view(np.uint64)), variant
+            for want, got in zip(full, engine.normalize_batch(A, b)):
+                assert np.array_equal(want.view(np.uint64), got.view(np.uint64)), variant
+    finally:
+        lib.pb200_normalize_variant(-2)
+
+
 @pytest.mark.parametrize('m,d', [(6, 3), (16, 6), (32, 8), (64, 12), (64, 16), (100, 5)])
 def test_cheby_and_bbox_vs_oracle(m, d):
     from polytope_b200 import engine
