@@ -16,6 +16,9 @@ Printed JSON (one line, rank 0):
   roofline  the dominant kernel (row LPs): algorithmic bytes / its mean device
             time (CUDA events on the launch stream inside the library) against
             the measured HBM peak, plus the fp64 view that actually bounds it
+            and `ab_read`: the batched (A|b) read in isolation (the constructor-
+            normalisation kernel, bulk async copies) at the bench batch and on a
+            50x larger batch that streams from HBM (untimed extra, N = 1 ... rank 0)
   cpu_baseline  the oracle port (scipy/HiGHS, as the reference calls it) on a
             bounded sample of the same workload, all host cores (N = 1 only)
 
@@ -312,6 +315,7 @@ def run_gpu(args):
                               'note': 'the path is fp64 latency/issue bound, not HBM bound (SURVEY.md 8d)'}},
         'cpu_baseline': cpu_baseline,
     }
+    line['roofline']['ab_read'] = ab_read_roofline(P, m, d, stages.get('normalize'), hbm_peak)
     traffic_file = os.path.join(ROOT, 'profiles', 'row_lp_dram_bytes.json')
     if os.path.exists(traffic_file):
         try:
@@ -322,6 +326,45 @@ def run_gpu(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ab_read_roofline(P, m, d, stage_ms, hbm_peak, scale=50, reps=6):
+    """The batched (A|b) read in isolation (north_star's HBM target applies to this phase):
+    the constructor-normalisation kernel reads A, b once and writes An, bn, valid once.  Reported at
+    the bench batch (stage time of the timed steps, launch-latency sized: 46 MB) and, outside the
+    timed region, on a batch `scale` times larger that streams from HBM (inputs >> L2)."""
+    import torch
+    from polytope_b200 import _capi
+    per_poly = 2 * 8 * m * (d + 1) + 8
+    out = {'kernel': 'normalize_tile_kernel<bulk copies> (Polytope.__init__ normalisation of the stacked batch)',
+           'algorithmic_bytes_per_polytope': per_poly, 'peak': hbm_peak, 'unit': 'GB/s'}
+    if stage_ms:
+        out['bench_batch'] = {'n_poly': P, 'ms': stage_ms, 'achieved': per_poly * P / stage_ms / 1e6,
+                              'frac': per_poly * P / stage_ms / 1e6 / hbm_peak}
+    Pb = P * scale
+    lib = _capi.lib()
+    A = torch.randn(Pb, m, d, dtype=torch.float64, device='cuda')
+    b = torch.randn(Pb, m, dtype=torch.float64, device='cuda')
+    An, bn = torch.empty_like(A), torch.empty_like(b)
+    valid = torch.empty(Pb, dtype=torch.int64, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    ms = []
+    for k in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = lib.pb200_normalize_batch(A.data_ptr(), b.data_ptr(), None, Pb, m, d, An.data_ptr(), bn.data_ptr(),
+                                       valid.data_ptr(), st)
+        e1.record()
+        torch.cuda.synchronize()
+        if rc != 0:
+            raise RuntimeError('pb200_normalize_batch failed: %d' % rc)
+        if k >= 2:
+            ms.append(e0.elapsed_time(e1))
+    mean = sum(ms) / len(ms)
+    out['streaming_batch'] = {'n_poly': Pb, 'bytes': per_poly * Pb, 'ms': mean, 'achieved': per_poly * Pb / mean / 1e6,
+                              'frac': per_poly * Pb / mean / 1e6 / hbm_peak,
+                              'note': 'untimed extra after the steps; inputs 1.15 GB >> L2, CUDA events per launch'}
+    return out
 
 
 def main():
