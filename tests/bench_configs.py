@@ -2,7 +2,10 @@
 """Throughput + parity sample for the BASELINE configs other than the headline
 (cfg3 Region members / pairwise intersect, cfg4 d=12 m=64 reduce, cfg5 adjacency
 grid).  Device-timed with CUDA events, batch resident in HBM, 3 warm-ups.
-Prints one JSON object; commit the output under profiles/."""
+Prints one JSON object; commit the output under profiles/.
+
+Lives under tests/ because it samples the oracle as its parity checker (only tests/, smoke() and
+bench.py's CPU arm may touch oracle/); the timed region never does."""
 import json
 import os
 import sys

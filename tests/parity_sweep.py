@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Large-sample parity sweep: GPU reduce() keep masks / flags / LP counts against the CPU
-oracle (multiprocessing over the host cores).  Usage: parity_sweep.py [n_cfg2 n_cfg4 n_cfg3]"""
+oracle (multiprocessing over the host cores).  Usage: tests/parity_sweep.py [n_cfg2 n_cfg4 n_cfg3]
+(test infrastructure: lives under tests/ because it runs the oracle as the checker)"""
 import json
 import multiprocessing as mp
 import os

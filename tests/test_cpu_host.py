@@ -69,6 +69,19 @@ def test_product_never_imports_oracle_or_scipy():
                 assert not re.search(r'linprog\s*\(', src), f
 
 
+def test_oracle_is_only_reachable_from_the_checkers():
+    """oracle/ is test infrastructure: besides tests/, only smoke() and bench.py's CPU arm import it,
+    and bench.py does so inside the CPU-arm functions, never at module level."""
+    for f in os.listdir(os.path.join(REPO, 'tools')) + ['workloads.py']:
+        if f.endswith('.py'):
+            path = os.path.join(REPO, 'tools', f) if f != 'workloads.py' else os.path.join(REPO, f)
+            assert not re.search(r'^\s*(from|import)\s+oracle', open(path).read(), re.M), f
+    bench = open(os.path.join(REPO, 'bench.py')).read()
+    assert not re.search(r'^(from|import)\s+oracle', bench, re.M)
+    users = re.findall(r'^def (\w+)\([^\n]*\n(?:(?!^def ).*\n)*?\s+from oracle import', bench, re.M)
+    assert users and all('cpu' in u or 'reference' in u or 'oracle' in u for u in users), users
+
+
 def test_polytope_constructor_matches_reference_normalisation(golden):
     """Polytope.__init__ vs the oracle's restatement of polytope.py:122-138."""
     import polytope_b200 as pb
