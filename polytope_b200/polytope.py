@@ -16,6 +16,7 @@ rotation, plotting) are not provided.
 """
 import logging
 import math
+import warnings
 
 import numpy as np
 
@@ -591,6 +592,43 @@ def adjacency_matrix(cells, abs_tol=ABS_TOL):
     adj[i, j] = flags
     adj[j, i] = flags
     return adj
+
+
+def separate(reg1, abs_tol=ABS_TOL):
+    """Divide a Region into connected Regions (polytope.py:1795-1824).
+
+    The reference grows each part with one is_adjacent(part, polytope) call per
+    remaining polytope -- O(n^2) sequential LPs.  Here all n(n-1)/2 pair LPs run
+    as one `adjacency_matrix` launch and the reference's grouping is replayed on
+    the flags: a single ordered pass per part (a polytope skipped before the
+    part reached it is not revisited, so a part is not always a full connected
+    component -- same as the reference), members in the order they were added,
+    props copied.  As in the reference (:1815) the pair test runs at the default
+    tolerance; `abs_tol` is accepted and unused.
+    """
+    polys = list(reg1.list_poly)
+    adj = adjacency_matrix(polys)
+    final = []
+    left = list(range(len(polys)))
+    while left:
+        members = [left[0]]
+        for j in left[1:]:
+            if adj[members, j].any():
+                members.append(j)
+        part = Region([polys[k] for k in members], [])
+        part.props = reg1.props.copy()
+        final.append(part)
+        taken = set(members)
+        left = [k for k in left if k not in taken]
+    return final
+
+
+def is_inside(polyreg, point, abs_tol=ABS_TOL):
+    """`point in polyreg` (deprecated in the reference too, polytope.py:1017-1029)."""
+    warnings.warn('Write `point in polyreg` instead of calling this function.', DeprecationWarning)
+    if not isinstance(point, np.ndarray):
+        point = np.array(point)
+    return polyreg.contains(point[:, np.newaxis], abs_tol)[0]
 
 
 # ---------------------------------------------------------------------------

@@ -113,3 +113,36 @@ def box_rows(intervals):
 
 
 DIFF_CASES = 30
+
+
+def partition_scenarios():
+    """Inputs of `separate` / `find_adjacent_regions` (tests/golden/make_golden_partition.py):
+    a list of (name, cells, groups) with cells = [(A, b), ...] and groups = ordered lists of
+    cell indices, one per region.  `separate` is recorded for every group, the adjacency matrix
+    for the partition formed by all groups of a scenario."""
+    out = []
+
+    def boxes(coords):
+        return [box_rows([[c, c + 1.0] for c in xy]) for xy in coords]
+
+    # chain listed out of order: the reference's single ordered pass splits a connected set
+    out.append(('chain_out_of_order', boxes([(0, 0), (2, 0), (1, 0), (5, 5)]), [[0, 1, 2], [3]]))
+    # corner contact counts as adjacent (both polytopes are inflated by abs_tol)
+    out.append(('corner_contact', boxes([(0, 0), (1, 1), (3, 0), (2, 1), (0, 3)]), [[0, 1, 2, 3, 4]]))
+    rng = np.random.default_rng(77)
+    for k, shape in enumerate([(4, 4), (3, 3, 3), (5, 4), (2, 2, 2, 2)]):
+        A, b, _ = box_grid(shape)
+        n = len(A)
+        pick = rng.permutation(n)[: max(6, (2 * n) // 3)]
+        label = rng.integers(0, 4, len(pick))
+        groups = [[int(i) for i in range(len(pick)) if label[i] == g] for g in range(4)]
+        out.append(('grid%d' % k, [(A[i], b[i]) for i in pick], [g for g in groups if g]))
+    for k, (m, d, n) in enumerate([(6, 2, 9), (8, 3, 8)]):      # overlapping / disjoint general polytopes
+        cells = []
+        for i in range(n):
+            A, b = box_cuts(9100 + 10 * k + i, m, d)
+            cells.append((A, 0.45 * b + A @ rng.uniform(-1.6, 1.6, d)))
+        label = rng.integers(0, 3, n)
+        groups = [[int(i) for i in range(n) if label[i] == g] for g in range(3)]
+        out.append(('general%d' % k, cells, [g for g in groups if g]))
+    return out
