@@ -337,6 +337,11 @@ def box2poly(box):
     return Polytope.from_box(box)
 
 
+def _bounding_box_to_polytope(lower, upper):
+    """Polytope of the box with the given corner columns (polytope.py:1303-1311)."""
+    return box2poly([(a[0], b[0]) for a, b in zip(lower, upper)])
+
+
 def is_empty(polyreg):
     """Structural emptiness, no LP (polytope.py:939-959)."""
     n = len(polyreg)

@@ -78,3 +78,15 @@ def test_is_inside_warns_and_goes_to_the_device():
         else:                                   # no CPU fallback: the call must fail loudly
             with pytest.raises(_capi.Pb200Error):
                 pb.is_inside(box, [0.5, 0.5])
+
+
+def test_bounding_box_to_polytope_rebuilds_the_box():
+    """Structure of reference test_bounding_box_to_polytope (tests/polytope_test.py:299-312); the
+    bounding-box LPs themselves are GPU work (tests/test_gpu_polytope.py)."""
+    import polytope_b200 as pb
+    from polytope_b200 import polytope as alg
+    for intervals in ([[0, 1]], [[0, 1], [0, 2]], [[-1, 2], [3, 5], [-5, -3]]):
+        iv = np.array(intervals, dtype=float)
+        poly = pb.box2poly(intervals)
+        back = alg._bounding_box_to_polytope(iv[:, :1], iv[:, 1:])
+        assert np.array_equal(back.A, poly.A) and np.array_equal(back.b, poly.b) and back.minrep
