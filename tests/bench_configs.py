@@ -195,6 +195,57 @@ def contains_bench(m=16, d=8, N=1 << 25):
             'flag_mismatches_vs_oracle': int((out[0, :100000].cpu().numpy() != ref).sum())}
 
 
+def cfg5_partition(shape=(32, 32), block=4, ref_regions=6):
+    """The is_adjacent callers on a box grid cut into block x block regions: find_adjacent_regions
+    (one launch over all n(n-1)/2 cell pairs, OR-ed per region pair) and separate() of the union of
+    every other region (disconnected by construction).  Wall-clock, host bookkeeping included; the
+    oracle's sequential loops are timed on the first `ref_regions` regions only."""
+    import polytope_b200 as pb
+    A, b, idx = wl.box_grid(shape)
+    cells = [pb.Polytope(A[i], b[i]) for i in range(len(A))]
+    label = (idx[:, 0] // block) * ((shape[1] + block - 1) // block) + idx[:, 1] // block
+    regions = [pb.Region([cells[i] for i in np.nonzero(label == g)[0]]) for g in range(int(label.max()) + 1)]
+    n_cells = len(cells)
+
+    def wall(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3, out
+
+    ms_adj, adj = wall(lambda: pb.find_adjacent_regions(regions))
+    every_other = pb.Region([p for g, reg in enumerate(regions) if g % 2 == 0 for p in reg.list_poly])
+    ms_sep, parts = wall(lambda: pb.separate(every_other))
+    # oracle: the reference's loop of is_adjacent(region_i, region_j), j < i, with its early exits
+    sub = regions[:ref_regions]
+    t0 = time.perf_counter()
+    ref = np.eye(len(sub), dtype=np.int8)
+    n_ref_lp = 0
+    for i in range(len(sub)):
+        for j in range(i):
+            hit = False
+            for p in sub[i]:
+                for q in sub[j]:
+                    n_ref_lp += 1
+                    if orc.is_adjacent(p.A, p.b, q.A, q.b):
+                        hit = True
+                        break
+                if hit:
+                    break
+            ref[i, j] = ref[j, i] = hit
+    ref_s = time.perf_counter() - t0
+    return {'workload': 'find_adjacent_regions / separate on a %s box grid in %dx%d regions (%d regions, %d cells)'
+                        % ('x'.join(map(str, shape)), block, block, len(regions), n_cells),
+            'find_adjacent_regions_ms': ms_adj, 'pair_LPs': n_cells * (n_cells - 1) // 2,
+            'pair_LPs_per_s_wall': n_cells * (n_cells - 1) // 2 / (ms_adj * 1e-3),
+            'separate_ms': ms_sep, 'separate_cells': len(every_other), 'separate_parts': len(parts),
+            'oracle_regions': len(sub), 'oracle_LPs': n_ref_lp, 'oracle_s': ref_s,
+            'oracle_mismatches': int((adj[:len(sub), :len(sub)] != ref).sum())}
+
+
 try:
     PEAK_HBM = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
 except (OSError, ValueError, KeyError):
@@ -212,6 +263,6 @@ if __name__ == '__main__':
         sys.exit(0)
     t0 = time.time()
     out = {'cfg3': cfg3(), 'cfg4': cfg4(), 'd16': cfg4(500, 64, 16), 'cfg5': cfg5(),
-           'cfg5_4d': cfg5((6, 6, 6, 6))}
+           'cfg5_4d': cfg5((6, 6, 6, 6)), 'cfg5_partition': cfg5_partition()}
     out['wall_s'] = time.time() - t0
     print(json.dumps(out, indent=1))
