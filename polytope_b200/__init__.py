@@ -16,7 +16,7 @@ from polytope_b200.polytope import (
     volume, volume_batch, grid_region, enumerate_integral_points,
     qhull, qhull_batch, extreme, extreme_batch,
     envelope, is_convex, is_subset, union, region_diff, region_diff_batch, mldivide,
-    separate, is_inside)
+    separate, is_inside, is_interior)
 from polytope_b200.prop2partition import find_adjacent_regions
 
 __version__ = '0.1.0'

@@ -628,6 +628,21 @@ def separate(reg1, abs_tol=ABS_TOL):
     return final
 
 
+def is_interior(r0, r1, abs_tol=ABS_TOL):
+    """polytope.py:1888-1909, kept verbatim in meaning: True as soon as some polytope of r1,
+    enlarged by abs_tol, is NOT a subset of r0 (the reference's docstring promises the opposite;
+    callers get what the reference returns).  One `<=` (region_diff search + volume) per member."""
+    if isinstance(r0, Polytope):
+        r0 = Region([r0])
+    if isinstance(r1, Polytope):
+        r1 = Region([r1])
+    for p in r1:
+        dummy = Polytope(p.A.copy(), p.b.copy() + abs_tol)
+        if not dummy <= r0:
+            return True
+    return False
+
+
 def is_inside(polyreg, point, abs_tol=ABS_TOL):
     """`point in polyreg` (deprecated in the reference too, polytope.py:1017-1029)."""
     warnings.warn('Write `point in polyreg` instead of calling this function.', DeprecationWarning)
