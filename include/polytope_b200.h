@@ -90,8 +90,10 @@ int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows,
  * the duplicate-direction filter (:1094-1112), both early exits (:1114-1116,
  * :1135-1138), the bounding-box prefilter (:1118-1134) and the per-row LP loop
  * (:1142-1160) with its +0.1/-0.1 one-ulp drift of b.
- *   normalize != 0: (A, b) are raw constructor arguments; == 0: they are the
- *             .A/.b of an existing Polytope and are used as they are
+ *   normalize: bit field.  PB200_REDUCE_NORMALIZE (1): (A, b) are raw constructor
+ *             arguments; clear: they are the .A/.b of an existing Polytope and are
+ *             used as they are.  PB200_REDUCE_NO_EARLY_EXIT (2): the reference's
+ *             `nonEmptyBounded=0` -- the two `neq <= nx + 1` exits are skipped.
  *   keep[P]   bit i set iff input row i is kept
  *   flags[P]  PB200_F_* bits
  *   r[P], xc[P][d]  Chebyshev ball of the input (first is_fulldim call)
@@ -100,6 +102,8 @@ int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows,
  *   n_lp[P]         LPs the reference algorithm solves for this polytope
  *   lp_iters[P]     (nullable) interior-point iterations summed over those LPs
  *   workspace: pb200_reduce_workspace_bytes(P, m, d) bytes of device memory. */
+#define PB200_REDUCE_NORMALIZE 1
+#define PB200_REDUCE_NO_EARLY_EXIT 2
 size_t pb200_reduce_workspace_bytes(int P, int m, int d);
 int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows,
                        int P, int m, int d, double abs_tol, int normalize,

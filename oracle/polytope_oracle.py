@@ -171,7 +171,7 @@ def bbox_candidates(A, b, lb, ub):
     return cand.squeeze()
 
 
-def reduce(A, b, abs_tol=ABS_TOL, normalize=True):
+def reduce(A, b, abs_tol=ABS_TOL, normalize=True, non_empty_bounded=True):
     """Redundant-row removal, polytope.py:1053-1163, on raw (A, b).
 
     Returns a dict:
@@ -182,6 +182,8 @@ def reduce(A, b, abs_tol=ABS_TOL, normalize=True):
       minrep  -- value of the returned object's `minrep`
       r, xc   -- Chebyshev ball found by the leading is_fulldim() call
       n_lp    -- LPs this call solved
+      margins -- decision quantity `-fun - h[k]` of every row LP that ended with status 0
+                 (compared with abs_tol at :1153; lets tests count "ambiguous" LPs)
     """
     global lp_count
     lp0 = lp_count
@@ -193,7 +195,7 @@ def reduce(A, b, abs_tol=ABS_TOL, normalize=True):
         idx = np.arange(A.shape[0])
     r, xc = cheby_ball(A, b)
     out = dict(empty=False, keep=[], A=None, b=None, minrep=False,
-               r=r, xc=xc, n_lp=0)
+               r=r, xc=xc, n_lp=0, margins=[])
     if not r > ABS_TOL:                 # is_fulldim(poly) uses its default, :1081
         out['empty'] = True
         out['n_lp'] = lp_count - lp0
@@ -203,14 +205,14 @@ def reduce(A, b, abs_tol=ABS_TOL, normalize=True):
     keep = duplicate_rows(A, b, abs_tol)                  # :1094-1112
     A, b, idx = A[keep], b[keep], idx[keep]
     neq, nx = A.shape
-    done = neq <= nx + 1                                  # :1114-1116
+    done = non_empty_bounded and neq <= nx + 1            # :1113-1116
     if not done and neq > 3 * nx:                         # :1118-1134
         An, bn, _ = normalize_rows(A, b)                  # Polytope(A_arr,b_arr)
         lb, ub = bounding_box(An, bn)
         cand = bbox_candidates(A, b, lb, ub)
         A, b, idx = A[cand], b[cand], idx[cand]
         neq, nx = A.shape
-    done = done or neq <= nx + 1                          # :1135-1138
+    done = done or (non_empty_bounded and neq <= nx + 1)  # :1135-1138
     if done:
         out.update(keep=idx.tolist(), A=A, b=b, n_lp=lp_count - lp0)
         return out
@@ -221,6 +223,7 @@ def reduce(A, b, abs_tol=ABS_TOL, normalize=True):
         sol = lpsolve(-A[k, :], A, h)
         h[k] -= 0.1
         if sol['status'] == 0:
+            out['margins'].append(float(-sol['fun'] - h[k]))
             if (-sol['fun'] - h[k]) > abs_tol:
                 kept.append(k)
         elif sol['status'] == 3:

@@ -536,13 +536,14 @@ constexpr uint32_t CTL_ROW_LOOP = 1u << 17;
 constexpr uint32_t CTL_MASK = 0xffff0000u;
 
 // decide early exit / bbox need after the duplicate filter (polytope.py:1113-1118)
-__global__ void plan_kernel(const uint64_t* __restrict__ rows1, uint32_t* __restrict__ flags, int P, int d) {
+__global__ void plan_kernel(const uint64_t* __restrict__ rows1, uint32_t* __restrict__ flags, int P, int d,
+                            int early_exit) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     uint32_t f = flags[p];
     if (f & PB200_F_EMPTY) return;
     const int neq = __popcll(rows1[p]);
-    if (neq <= d + 1) { flags[p] = f; return; }              // early exit, minrep stays False
+    if (early_exit && neq <= d + 1) { flags[p] = f; return; }    // nonEmptyBounded early exit, minrep stays False
     if (neq > 3 * d) f |= CTL_NEED_BBOX | PB200_F_BBOX;
     else f |= CTL_ROW_LOOP;
     flags[p] = f;
@@ -552,7 +553,7 @@ __global__ void plan_kernel(const uint64_t* __restrict__ rows1, uint32_t* __rest
 __global__ void candidate_kernel(const double* __restrict__ An, const double* __restrict__ bn,
                                  const uint64_t* __restrict__ rows1, const double* __restrict__ bblo,
                                  const double* __restrict__ bbhi, const int8_t* __restrict__ bbstatus, int P, int m, int d,
-                                 uint64_t* __restrict__ rows2, uint32_t* __restrict__ flags) {
+                                 int early_exit, uint64_t* __restrict__ rows2, uint32_t* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (p >= P) return;
@@ -593,7 +594,7 @@ __global__ void candidate_kernel(const double* __restrict__ An, const double* __
         rows2[p] = mask2;
         uint32_t g = f & ~CTL_NEED_BBOX;
         if (lpfail) g |= PB200_F_LPFAIL;
-        if (__popcll(mask2) > d + 1) g |= CTL_ROW_LOOP;
+        if (!early_exit || __popcll(mask2) > d + 1) g |= CTL_ROW_LOOP;
         flags[p] = g;
     }
 }
@@ -761,6 +762,8 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     if (ws.bytes > workspace_bytes) return fail(PB200_EWORKSPACE, "pb200_reduce_batch: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     double* An = A_out ? A_out : ws.An;
+    const int early_exit = (normalize & PB200_REDUCE_NO_EARLY_EXIT) ? 0 : 1;
+    normalize &= PB200_REDUCE_NORMALIZE;
     int rc;
     if (lp_iters) PB_CHECK_CUDA(cudaMemsetAsync(lp_iters, 0, sizeof(int32_t) * P, st));
     stage_mark(0, st);
@@ -776,11 +779,13 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     {
         const int wpb = 4;
         const size_t sh = (size_t)wpb * (m * d + 2 * m) * sizeof(double);
+        if (sh > 48 * 1024)
+            PB_CHECK_CUDA(cudaFuncSetAttribute(prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
         prefilter_kernel<<<blocks_for(P, wpb), wpb * 32, sh, st>>>(An, ws.bn, ws.valid, r, ws.cheb_status, P, m, d,
                                                                  abs_tol, ws.rows1, flags);
         ++g_launches;
         PB_CHECK_CUDA(cudaGetLastError());
-        plan_kernel<<<blocks_for(P, 256), 256, 0, st>>>(ws.rows1, flags, P, d);
+        plan_kernel<<<blocks_for(P, 256), 256, 0, st>>>(ws.rows1, flags, P, d, early_exit);
         ++g_launches;
         PB_CHECK_CUDA(cudaGetLastError());
     }
@@ -791,7 +796,7 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     stage_mark(4, st);
     // 5. candidate filter
     candidate_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(An, ws.bn, ws.rows1, ws.bblo, ws.bbhi, ws.bbstatus,
-                                                                       P, m, d, ws.rows2, flags);
+                                                                       P, m, d, early_exit, ws.rows2, flags);
     ++g_launches;
     PB_CHECK_CUDA(cudaGetLastError());
     stage_mark(5, st);

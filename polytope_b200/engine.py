@@ -6,10 +6,15 @@ to the device on the current CUDA stream, results come back as numpy arrays).
 torch is plumbing only: device memory, streams.  All arithmetic happens in
 libpolytope_b200.so; there is no fallback.
 """
+import logging
+import threading
+
 import numpy as np
 import torch
 
 from polytope_b200 import _capi
+
+logger = logging.getLogger(__name__)
 
 F_EMPTY, F_MINREP, F_BBOX, F_LPFAIL = 1, 2, 4, 8
 ABS_TOL = 1e-7          # polytope/polytope.py:83
@@ -144,7 +149,8 @@ class ReduceResult(object):
         return [np.nonzero(row)[0].tolist() for row in bits]
 
 
-def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True, want_b=True):
+def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True, want_b=True,
+                 non_empty_bounded=True):
     """reduce(Polytope(A[p], b[p])) for every p (polytope.py:1053-1163).
 
     normalize=False reproduces reduce(poly) on rows that a constructor already
@@ -172,7 +178,8 @@ def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True
     ws_bytes = lib.pb200_reduce_workspace_bytes(P, m, d)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device='cuda')
     _capi.check(lib.pb200_reduce_batch(
-        A.data_ptr(), b.data_ptr(), mr_ptr, P, m, d, float(abs_tol), int(bool(normalize)),
+        A.data_ptr(), b.data_ptr(), mr_ptr, P, m, d, float(abs_tol),
+        int(bool(normalize)) | (0 if non_empty_bounded else REDUCE_NO_EARLY_EXIT),
         keep.data_ptr(), flags.data_ptr(), r.data_ptr(), xc.data_ptr(), b_out.data_ptr(),
         A_out.data_ptr() if want_A else 0, n_lp.data_ptr(), lp_iters.data_ptr(), ws.data_ptr(),
         ws_bytes, _stream()),
@@ -181,12 +188,23 @@ def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True
     outs = _out(host, *outs)
     res.keep, res.flags, res.r, res.xc, res.b, res.n_lp, res.lp_iters = outs[:7]
     res.A = outs[7] if want_A else None
+    if logger.isEnabledFor(logging.DEBUG):
+        it = np.asarray(res.lp_iters.cpu() if isinstance(res.lp_iters, torch.Tensor) else res.lp_iters)
+        nl = np.asarray(res.n_lp.cpu() if isinstance(res.n_lp, torch.Tensor) else res.n_lp)
+        per_lp = it / np.maximum(nl, 1)
+        logger.debug('reduce_batch: P=%d m=%d d=%d LPs=%d mean ipm iterations/LP=%.2f histogram(per polytope, '
+                     'bins 0..10+)=%s', P, m, d, int(nl.sum()), float(it.sum()) / max(int(nl.sum()), 1),
+                     np.bincount(np.minimum(per_lp.astype(int), 10), minlength=11).tolist())
     return res
 
 
+REDUCE_NO_EARLY_EXIT = 2        # bit 1 of pb200_reduce_batch's `normalize` argument (include/polytope_b200.h)
 PIPELINE_MIN_CHUNK = 1024      # polytopes per chunk below which pipelining does not pay
 PIPELINE_CHUNKS = int(__import__('os').environ.get('PB200_PIPELINE_CHUNKS', '2'))
-_pinned = {}
+PINNED_CACHE_BYTES = 1 << 30   # cap on cached page-locked staging memory (per process)
+_pinned = {}                   # tag -> flat uint8 pinned buffer (grown geometrically, reused through views)
+_pinned_lock = threading.Lock()
+_pipeline_lock = threading.Lock()   # the two pipeline streams and the staging buffers are shared
 _streams = []
 
 
@@ -195,20 +213,40 @@ def _is_host(x):
 
 
 def _pinned_buffer(tag, shape, dtype):
-    """Reusable pinned host buffer (cudaHostAlloc is far too slow to do per call)."""
-    key = (tag, tuple(shape), dtype)
-    buf = _pinned.get(key)
-    if buf is None:
-        buf = torch.empty(tuple(shape), dtype=dtype).pin_memory()
-        _pinned[key] = buf
-    return buf
+    """Reusable pinned host buffer (cudaHostAlloc is far too slow to do per call): one flat
+    page-locked allocation per tag, grown geometrically and handed out as a view, so varying
+    batch shapes do not accumulate allocations.  Requests that would push the cache past
+    PINNED_CACHE_BYTES are served by a one-off pinned allocation that is not kept."""
+    shape = tuple(int(v) for v in shape)
+    numel = 1
+    for v in shape:
+        numel *= v
+    nbytes = numel * torch.empty((), dtype=dtype).element_size()
+    with _pinned_lock:
+        flat = _pinned.get(tag)
+        if flat is None or flat.numel() < nbytes:
+            others = sum(v.numel() for k, v in _pinned.items() if k != tag)
+            want = max(nbytes, 2 * flat.numel() if flat is not None else 0)
+            if others + want > PINNED_CACHE_BYTES:
+                want = nbytes
+            if others + want > PINNED_CACHE_BYTES:
+                return torch.empty(shape, dtype=dtype).pin_memory()
+            flat = torch.empty(max(want, 16), dtype=torch.uint8).pin_memory()
+            _pinned[tag] = flat
+        return flat[:nbytes].view(dtype).view(shape)
 
 
-def _reduce_batch_host_pipelined(A, b, m_rows, abs_tol, normalize, want_A, want_b):
+def _reduce_batch_host_pipelined(A, b, m_rows, abs_tol, normalize, want_A, want_b, non_empty_bounded=True):
     """reduce_batch for host-resident batches: the batch is cut into chunks that
     alternate between two CUDA streams, so the H2D copy of chunk k+1 and the D2H
     of chunk k-1 overlap the kernels of chunk k.  Results land in pinned host
     buffers and come back as numpy arrays."""
+    with _pipeline_lock:
+        return _reduce_batch_host_pipelined_locked(A, b, m_rows, abs_tol, normalize, want_A, want_b,
+                                                   non_empty_bounded)
+
+
+def _reduce_batch_host_pipelined_locked(A, b, m_rows, abs_tol, normalize, want_A, want_b, non_empty_bounded):
     if not _streams:
         _streams.extend([torch.cuda.Stream(), torch.cuda.Stream()])
     At = torch.as_tensor(A)
@@ -236,7 +274,8 @@ def _reduce_batch_host_pipelined(A, b, m_rows, abs_tol, normalize, want_A, want_
             Ad = At[lo:hi].to('cuda', non_blocking=True)
             bd = bt[lo:hi].to('cuda', non_blocking=True)
             md = None if mt is None else mt[lo:hi].to('cuda', non_blocking=True)
-            res = reduce_batch(Ad, bd, md, abs_tol=abs_tol, normalize=normalize, want_A=want_A)
+            res = reduce_batch(Ad, bd, md, abs_tol=abs_tol, normalize=normalize, want_A=want_A,
+                               non_empty_bounded=non_empty_bounded)
             for n in names:
                 out[n][lo:hi].copy_(getattr(res, n), non_blocking=True)
             keepalive.append((Ad, bd, md, res))
@@ -492,7 +531,7 @@ class DiffResult(object):
 
 
 def region_diff_batch(PA, Pb, RA, Rb, p_rows=None, r_rows=None, n_reg=None, abs_tol=ABS_TOL,
-                      intersect_tol=ABS_TOL, piece_cap=None, max_tries=4):
+                      intersect_tol=ABS_TOL, piece_cap=None, max_tries=16):
     """poly_t \\ region_t for T problems (polytope.py:2117-2282).
 
     PA[T, mp, d], Pb[T, mp]; RA[T, Nr, mr, d], Rb[T, Nr, mr] -- or RA[Nr, mr, d],
@@ -533,9 +572,15 @@ def region_diff_batch(PA, Pb, RA, Rb, p_rows=None, r_rows=None, n_reg=None, abs_
         n_used = int(used.item())
         if n_used <= cap:
             break
-        cap = n_used
+        # a search stops at its first overflowing piece, so `used` under-reports the need
+        # (cap + one per overflowed problem): grow geometrically, not to `used`
+        logger.debug('region_diff_batch: piece pool of %d overflowed (%d requested), retrying with %d',
+                     cap, n_used, max(n_used, 4 * cap))
+        cap = max(n_used, 4 * cap)
+        del pA, pb, prow, pred, pown, pseq
     else:
-        raise _capi.Pb200Error('region_diff_batch: piece pool still too small')
+        raise _capi.Pb200Error('region_diff_batch: piece pool still too small after %d tries (cap=%d)'
+                               % (max_tries, cap))
     # pool order is arrival order: sort by (owner, seq)
     key = pown[:n_used].to(torch.int64) * (1 << 31) + pseq[:n_used].to(torch.int64)
     order = torch.argsort(key)

@@ -431,8 +431,8 @@ def bounding_box_batch(polys):
     return [p.bbox for p in polys]
 
 
-def reduce_batch(polys, abs_tol=ABS_TOL):
-    """[reduce(p, abs_tol=abs_tol) for p in polys] through the device pipeline."""
+def reduce_batch(polys, abs_tol=ABS_TOL, nonEmptyBounded=1):
+    """[reduce(p, nonEmptyBounded, abs_tol) for p in polys] through the device pipeline."""
     out = [None] * len(polys)
     todo = []
     for k, p in enumerate(polys):
@@ -446,10 +446,17 @@ def reduce_batch(polys, abs_tol=ABS_TOL):
             todo.append(k)
     if todo:
         A, b, rows = _stack([polys[k] for k in todo])
-        res = engine.reduce_batch(A, b, rows, abs_tol=abs_tol, normalize=False)
+        res = engine.reduce_batch(A, b, rows, abs_tol=abs_tol, normalize=False,
+                                  non_empty_bounded=bool(nonEmptyBounded))
         keeps = res.keep_lists()
         for t, k in enumerate(todo):
             p = polys[k]
+            if res.flags[t] & engine.F_LPFAIL and not (res.flags[t] & engine.F_EMPTY):
+                # reduce() -> Polytope(A_arr, b_arr).bounding_box raises on LP status 1 / 4
+                # (polytope.py:1382, :1404); a failed row LP is dropped silently there (:1152-1160),
+                # but it is surfaced here rather than returning a polytope built on a failed solve
+                raise RuntimeError('reduce: `polytope_b200.solvers.lpsolve` did not converge for an LP of '
+                                   'polytope {k} of the batch (status 1 or 4)'.format(k=k))
             if p.fulldim is None:      # is_fulldim(poly) side effects, polytope.py:1081
                 rr = res.r[t]
                 _store_cheby(p, 0 if rr == rr else 4, rr, res.xc[t])
@@ -517,9 +524,7 @@ def reduce(poly, nonEmptyBounded=1, abs_tol=ABS_TOL):
         if len(lst) > 0:
             return Region(lst, poly.props)
         return Polytope()
-    if not nonEmptyBounded:
-        raise NotImplementedError('reduce(nonEmptyBounded=0) is outside the B200 hot path')
-    return reduce_batch([poly], abs_tol=abs_tol)[0]
+    return reduce_batch([poly], abs_tol=abs_tol, nonEmptyBounded=nonEmptyBounded)[0]
 
 
 def intersect(poly1, poly2, abs_tol=ABS_TOL):

@@ -148,3 +148,24 @@ def test_region_diff_with_many_cells_prefilters_on_the_host():
     # is_subset against the big region goes through the same path
     assert pc.is_subset(pc.box2poly([[1.5, 3.5], [2.5, 3.5]]), reg)
     assert not pc.is_subset(pc.box2poly([[14.5, 15.5], [2.5, 3.5]]), reg)
+
+
+def test_region_diff_piece_pool_grows_until_it_fits():
+    """1000 boxes each minus an inner box need 2 d = 6 pieces per problem, more than the initial
+    pool of max(4 T, 1024): the retry path must grow geometrically (growing to the
+    reported `used` only adds ~T per try and gave up after 4)."""
+    from polytope_b200 import engine
+    T, d = 1000, 3
+    rng = np.random.default_rng(3)
+    lo = rng.uniform(-1, 0, (T, d))
+    PA = np.broadcast_to(np.vstack([np.eye(d), -np.eye(d)]), (T, 2 * d, d)).copy()
+    Pb = np.hstack([lo + 3.0, -lo])
+    RA = PA[:, None].copy()
+    Rb = np.hstack([lo + 2.0, -(lo + 1.0)])[:, None].copy()
+    res = engine.region_diff_batch(PA, Pb, RA, Rb)
+    assert np.all(res.status == engine.DIFF_PIECES)
+    assert np.all(res.n_pieces == 2 * d)
+    assert len(res.A) == 2 * d * T
+    # tiny explicit pool: same result after several growth rounds
+    res2 = engine.region_diff_batch(PA, Pb, RA, Rb, piece_cap=64)
+    assert np.array_equal(res2.n_pieces, res.n_pieces) and np.array_equal(res2.A, res.A)

@@ -369,3 +369,37 @@ def test_host_batches_are_pipelined_and_equal_the_device_path():
                                want_A=False, want_b=False)
     assert slim.A is None and slim.b is None and np.array_equal(slim.keep, host.keep)
     assert slim.keep_lists() == host.keep_lists()
+
+
+def test_reduce_non_empty_bounded_zero_skips_the_early_exits():
+    """reduce(poly, nonEmptyBounded=0): the two `neq <= nx + 1` exits (polytope.py:1113-1116,
+    :1135-1138) are skipped, so small polytopes go through the row LPs and come back minrep."""
+    import polytope_b200 as pc
+    from polytope_b200 import engine
+    from oracle import polytope_oracle as orc
+    cases = [(np.array([[1., 0], [-1, 0], [0, 1]]), np.array([1., 1., 1.])),                    # m <= d+1, unbounded
+             (np.array([[1., 0], [-1, 0], [0, 1], [0, -1]]), np.array([1., 1., 1., 1.]))]
+    for i in range(6):
+        cases.append(wl.box_cuts(7700 + i, 10 + i, 3, True))
+    for A, b in cases:
+        res = engine.reduce_batch(A[None], b[None], non_empty_bounded=False)
+        o = orc.reduce(A, b, non_empty_bounded=False)
+        assert res.keep_lists()[0] == o['keep']
+        assert int(res.n_lp[0]) == o['n_lp']
+        assert bool(res.flags[0] & engine.F_MINREP) == o['minrep']
+        red = pc.reduce(pc.Polytope(A, b), nonEmptyBounded=0)
+        assert red.minrep == o['minrep'] and len(red.b) == len(o['keep'])
+
+
+def test_reduce_at_the_largest_advertised_shape():
+    """m = 64, d = 31 (n = 32 Chebyshev LP): the prefilter kernel needs > 48 KB of dynamic shared
+    memory there; keep sets against the oracle."""
+    from polytope_b200 import engine
+    from oracle import polytope_oracle as orc
+    A, b = wl.box_cuts_batch(15, 3, 64, 31)
+    res = engine.reduce_batch(A, b)
+    for i in range(len(A)):
+        o = orc.reduce(A[i], b[i])
+        assert res.keep_lists()[i] == o['keep']
+        assert int(res.n_lp[i]) == o['n_lp']
+        assert abs(res.r[i] - o['r']) <= 1e-9

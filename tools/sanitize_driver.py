@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Small batches through every kernel family, for compute-sanitizer (tools/sanitize.sh):
+lp_kernel_small (n <= 8), lp_kernel (n = 13), the reduce pipeline, adjacency, diff_kernel,
+hull_kernel, contains / volume.  Results are checked for plausibility only; parity is tests/."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import workloads as wl                      # noqa: E402
+from polytope_b200 import engine            # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+if which in ('all', 'lp_small'):
+    A, b = wl.box_cuts_batch(2, 6, 32, 8)
+    res = engine.reduce_batch(A, b)
+    assert not np.any(res.flags & engine.F_LPFAIL) and np.all(res.n_lp > 17)
+    Ag, bg, _ = wl.box_grid((3, 3))
+    adj, rad, st = engine.adjacent_pairs(Ag, bg)
+    assert int(adj.sum()) == 20
+if which in ('all', 'lp_generic'):
+    A, b = wl.box_cuts_batch(4, 3, 64, 12)
+    res = engine.reduce_batch(A, b)
+    assert not np.any(res.flags & engine.F_LPFAIL)
+    A, b = wl.box_cuts_batch(4, 2, 100, 5)
+    r, xc, st = engine.cheby_batch(A, b)
+    assert np.all(st == 0)
+if which in ('all', 'diff'):
+    import polytope_b200 as pc
+    out = pc.region_diff(pc.box2poly([[0, 3], [0, 3]]), pc.Region([pc.box2poly([[1, 2], [1, 2]])]))
+    assert len(out) == 4
+if which in ('all', 'hull'):
+    pts = wl.hull_points(1, 24, 4)
+    h = engine.hull_batch(pts[None])
+    assert int(h.status[0]) == 0 and int(h.facet_cnt[0]) > 8
+if which in ('all', 'sets'):
+    A, b = wl.box_cuts(5, 16, 4)
+    pts = wl.contains_points(3, 4, 1000)
+    fl = engine.contains_batch(A[None], b[None], pts)
+    assert fl.shape == (1, 1000)
+print('sanitize_driver ok:', which)
