@@ -258,6 +258,11 @@ int pb200_profile_read(float* stage_ms, int n);
  * identical bits; tools/normalize_bench.py measures them. */
 void pb200_normalize_variant(int variant);
 
+/* Diagnostics: the reduce / bounding-box LPs of polytopes with d <= 8 and m <= 64 run on the
+ * lane solver (one LP per lane, csrc/lp_lane.cuh); on = 0 sends them back to the warp-per-LP
+ * kernels for A/B measurements.  Default on. */
+void pb200_lane_solver(int on);
+
 /* Number of kernels this library has launched since load (bench.py's
  * `gpu_launches` evidence). */
 long long pb200_launch_count(void);

@@ -28,6 +28,7 @@ SIGNATURES = {
                            + [c_void_p] * 9 + [c_size_t, c_void_p]),
     'pb200_profile_enable': (None, [c_int]),
     'pb200_normalize_variant': (None, [c_int]),
+    'pb200_lane_solver': (None, [c_int]),
     'pb200_profile_read': (c_int, [c_void_p, c_int]),
     'pb200_contains_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_longlong, c_double, c_int,
                                      c_void_p, c_void_p]),

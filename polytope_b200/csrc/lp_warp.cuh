@@ -44,6 +44,12 @@ constexpr int LP_MAX_N = 32;            // columns (n-vectors are lane-owned)
 constexpr double LP_FEAS_TOL = 1e-9;
 constexpr double LP_GAP_TOL = 1e-9;
 constexpr double LP_STEP = 0.99;
+// Near-parallel active rows leave the dual residual stuck around 1e-8 (rounding amplified by the
+// conditioning of the active set) while the gap keeps shrinking: once the gap is four orders
+// below its tolerance, a dual residual of 1e-6 is accepted (cvxopt's and HiGHS' own feasibility
+// tolerance is 1e-7); the final polish still checks primal feasibility and the objective.
+constexpr double LP_STALL_DRES = 1e-6;
+constexpr double LP_STALL_GAP = 1e-13;
 #ifndef PB200_EARLY_TOL
 #define PB200_EARLY_TOL 1e-2
 #endif
@@ -215,6 +221,7 @@ __device__ __forceinline__ unsigned cholesky(const WarpScratch& w, int n, int la
     for (int k = 0; k < n; ++k) {
         const double p = w.M[k * L + k];
         const double p0 = __shfl_sync(FULL_MASK, dg, k);
+        __syncwarp();      // every lane has read the pivot before lane k overwrites it (racecheck, profiles/r02a_*)
         const bool ok = (p > 1e-13 * p0) && (p > 1e-30 * dmax) && (p > 1e-290) && (p < 1e300);
         double lik = 0.0;
         if (ok) {
@@ -468,7 +475,8 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
         if (pcost < 0.0) relgap = gap / -pcost;
         else if (dcost > 0.0) relgap = gap / dcost;
         if (PB_UNI(!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300))) { res.status = ST_NUMERICAL; break; }
-        const bool converged = pres <= LP_FEAS_TOL && dres <= LP_FEAS_TOL && (gap <= LP_GAP_TOL || relgap <= LP_GAP_TOL);
+        const bool converged = pres <= LP_FEAS_TOL && ((dres <= LP_FEAS_TOL && (gap <= LP_GAP_TOL || relgap <= LP_GAP_TOL)) ||
+                                                       (dres <= LP_STALL_DRES && (gap <= LP_STALL_GAP || relgap <= LP_STALL_GAP)));
         // At the loose tolerance the active set is usually already identified: try the
         // polish there and accept it only with a full optimality certificate (primal
         // feasible, active rows tight, y >= 0 with G_B'y + c = 0); otherwise keep
@@ -499,7 +507,21 @@ __device__ LpResult lp_solve_warp(const WarpScratch& w, int m, int n, double c, 
             }
             if (PB_UNI(cx < 0.0)) {
                 gxs2 = warp_sum(gxs2);
-                if (PB_UNI(sqrt(gxs2) / (-cx) * nc / nh <= 10.0 * LP_FEAS_TOL)) { res.status = ST_UNBOUNDED; break; }
+                if (PB_UNI(sqrt(gxs2) / (-cx) * nc / nh <= 10.0 * LP_FEAS_TOL)) {
+                    // improving recession direction: unbounded if feasible at all.  HiGHS reports 2 for
+                    // an LP that is infeasible as well, so restart on the feasibility problem (c = 0):
+                    // it ends with 3 (feasible) or with the infeasibility certificate
+                    lineal = true;
+                    c = 0.0;
+                    nc = 1.0;
+                    x = 0.0; tau = 1.0; kap = 1.0;
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r) {
+                        s[r] = live[r] ? fmax(h[r], 0.0) + 1.0 : 1.0;
+                        z[r] = live[r] ? 1.0 : 0.0;
+                    }
+                    continue;
+                }
             }
         }
         if (it == LP_MAX_ITER) break;

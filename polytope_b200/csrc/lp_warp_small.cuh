@@ -460,8 +460,10 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
             // relgap <= tol  <=>  gap <= tol * (-pcost)  or  gap <= tol * dcost
             const double gapref = pcost < 0.0 ? -pcost : (dcost > 0.0 ? dcost : 0.0);
             if (PB_UNI(!(mu == mu) || !(fabs(tau) < 1e300) || !(fabs(cx) < 1e300))) { res.status = ST_NUMERICAL; break; }
-            const bool converged = rz2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nh2 && rx2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nc2 &&
-                                   (gap <= LP_GAP_TOL || gap <= LP_GAP_TOL * gapref);
+            // (second alternative: see LP_STALL_* in lp_warp.cuh)
+            const bool converged = rz2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nh2 &&
+                                   ((rx2 * t2 <= LP_FEAS_TOL * LP_FEAS_TOL * nc2 && (gap <= LP_GAP_TOL || gap <= LP_GAP_TOL * gapref)) ||
+                                    (rx2 * t2 <= LP_STALL_DRES * LP_STALL_DRES * nc2 && (gap <= LP_STALL_GAP || gap <= LP_STALL_GAP * gapref)));
             // At the loose tolerance the active set is usually already identified:
             // try the polish there and accept it only with a full optimality
             // certificate (primal feasible, active rows tight, y >= 0 with
@@ -505,7 +507,23 @@ __device__ SmallResult lp_solve_small(const SmallScratch& w, int m, int n, doubl
                     const double gz2 = warp_sum(gzl * gzl);
                     if (PB_UNI(sqrt(gz2 * nh2 / nc2) <= 10.0 * LP_FEAS_TOL * (-hz))) { res.status = ST_INFEASIBLE; break; }
                 }
-                if (PB_UNI(cx < 0.0 && sqrt(gxs2 * nc2 / nh2) <= 10.0 * LP_FEAS_TOL * (-cx))) { res.status = ST_UNBOUNDED; break; }
+                if (PB_UNI(cx < 0.0 && sqrt(gxs2 * nc2 / nh2) <= 10.0 * LP_FEAS_TOL * (-cx))) {
+                    // unbounded if feasible at all: settle feasibility first (HiGHS reports 2 for an LP
+                    // that is infeasible as well) by restarting on the feasibility problem, c = 0
+                    lineal = true;
+                    cl = 0.0;
+                    nc2 = 1.0;
+                    xl = 0.0; tau = 1.0; kap = 1.0;
+                    if (own) { Xc[lane] = 0.0; Xx[lane] = 0.0; }
+#pragma unroll
+                    for (int r = 0; r < RPL; ++r) {
+                        s[r] = live[r] ? fmax(h[r], 0.0) + 1.0 : 1.0;
+                        z[r] = live[r] ? 1.0 : 0.0;
+                    }
+                    if (it == 0) it = 1;
+                    __syncwarp();
+                    continue;
+                }
             }
             if (it == LP_MAX_ITER) break;
         }

@@ -24,6 +24,7 @@
 #include "lp_warp_small.cuh"
 #include "staging.cuh"
 #include "normalize.cuh"
+#include "lane_kernel.cuh"
 
 namespace pb200 {
 
@@ -54,6 +55,7 @@ int sm_count() {
 // Problems
 // ------------------------------------------------------------------------
 struct GenericLP {
+    static constexpr bool kSnap = true;      // exact vertex coordinates on axis-aligned active rows
     const double *G, *h, *c;
     const int32_t* m_rows;
     int m, nn;
@@ -81,6 +83,7 @@ struct GenericLP {
 };
 
 struct ChebyLP {
+    static constexpr bool kSnap = false;
     const double *A, *b;
     const int32_t* m_rows;
     const uint64_t* rows;     // nullable row masks
@@ -120,6 +123,7 @@ struct ChebyLP {
 };
 
 struct BboxLP {
+    static constexpr bool kSnap = false;
     const double *A, *b;
     const int32_t* m_rows;
     const uint64_t* rows;        // nullable row masks
@@ -175,6 +179,7 @@ struct BboxLP {
 // surviving row of polytope p.  h reproduces the reference's in-place
 // `h[k] += 0.1; ...; h[k] -= 0.1`: rows before k carry the one-ulp drift.
 struct RowLP {
+    static constexpr bool kSnap = false;
     const double *A, *b;        // constructor-normalised
     const uint64_t* rows;       // surviving rows (after duplicate / bbox filters)
     uint32_t* flags;
@@ -235,6 +240,7 @@ struct RowLP {
 // is_adjacent, overlap=True (polytope.py:1856-1866): rows of both cells, b + tol,
 // constructor normalisation, Chebyshev LP, radius > tol/10.
 struct AdjacentLP {
+    static constexpr bool kSnap = false;
     const double *A, *b;
     int ncell, mc, d;
     const int32_t *pi, *pj;
@@ -312,7 +318,13 @@ __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long
         double c;
         double h[RPL];
         if (PB_UNI(!prob.template load<RPL>(t, w, lane, m, c, h, cached))) continue;
-        const LpResult res = lp_solve_warp<RPL>(w, m, n, c, h);
+        LpResult res = lp_solve_warp<RPL>(w, m, n, c, h);
+        if constexpr (Prob::kSnap) {
+            if (PB_UNI(res.status == ST_OPTIMAL)) {
+                res.x = snap_axis_rows<RPL>(w, w.u, m, n, lane, h, res.x);
+                res.fun = warp_sum(lane < n ? c * res.x : 0.0);
+            }
+        }
         prob.template store<RPL>(t, lane, res);
         __syncwarp();
     }
@@ -343,6 +355,12 @@ __global__ void __launch_bounds__(WPC * 32, PB200_SMALL_MINB) lp_kernel_small(co
         const SmallResult sr = lp_solve_small<RPL>(w, m, n, cl, h);
         LpResult res;
         res.status = sr.status; res.iters = sr.iters; res.fun = sr.fun; res.x = sr.x;
+        if constexpr (Prob::kSnap) {
+            if (PB_UNI(res.status == ST_OPTIMAL)) {
+                res.x = snap_axis_rows<RPL>(w, w.X, m, n, lane, h, res.x);
+                res.fun = warp_sum(lane < n ? cl * res.x : 0.0);
+            }
+        }
         prob.template store<RPL>(t, lane, res);
         __syncwarp();
     }
@@ -399,6 +417,39 @@ static int launch_lp(const Prob& prob, long long n_items, int m, int n, cudaStre
     if (m <= 32) return launch_lp_rpl<1>(prob, n_items, n, st);
     if (m <= 64) return launch_lp_rpl<2>(prob, n_items, n, st);
     return launch_lp_rpl<4>(prob, n_items, n, st);
+}
+
+// ------------------------------------------------------------------------
+// lane solver launch (LP families that share G: n <= 8 columns, m <= 64 rows)
+// ------------------------------------------------------------------------
+static int g_lane_enabled = 1;           // pb200_lane_solver(): A/B switch against the warp-per-LP kernels
+constexpr int LANE_COUNTERS = 256;
+__device__ unsigned long long g_lane_counters[LANE_COUNTERS];
+static unsigned long long* g_lane_counters_ptr = nullptr;
+static unsigned g_lane_ring = 0;
+
+static bool lane_applies(int m, int n) { return g_lane_enabled && n >= 1 && n <= LANE_NS && m >= 1 && m <= 64; }
+
+template <class Prob>
+static int launch_lanes(const Prob& prob, long long P, int m, cudaStream_t st) {
+    if (P <= 0) return PB200_OK;
+    if (!g_lane_counters_ptr) PB_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_lane_counters_ptr, g_lane_counters));
+    // one work counter per launch in flight (launches of different streams may overlap)
+    unsigned long long* counter = g_lane_counters_ptr + (__atomic_fetch_add(&g_lane_ring, 1u, __ATOMIC_RELAXED) % LANE_COUNTERS);
+    PB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    const size_t smem = lane_smem_doubles(m) * sizeof(double);
+    auto kern = lane_kernel<Prob>;
+    PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!sm_count()) return PB200_ECUDA;
+    int per_sm = 0;
+    PB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    if (per_sm < 1) return fail(PB200_EUNSUPPORTED, "lane LP kernel does not fit on an SM");
+    long long grid = (long long)g_sm_count * per_sm;      // persistent: one warp per CTA, all resident
+    if (P < grid) grid = P;
+    kern<<<(unsigned)grid, 32, smem, st>>>(prob, P, m, counter);
+    ++g_launches;
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
 }
 
 // ------------------------------------------------------------------------
@@ -533,6 +584,8 @@ __global__ void prefilter_kernel(const double* __restrict__ An, const double* __
 // pipeline control bits kept in the upper half of flags[] while reduce runs
 constexpr uint32_t CTL_NEED_BBOX = 1u << 16;
 constexpr uint32_t CTL_ROW_LOOP = 1u << 17;
+constexpr uint32_t CTL_RETRY_BBOX = 1u << 18;   // a lane-solver LP ended without a verdict: repeat on the warp kernel
+constexpr uint32_t CTL_RETRY_ROWS = 1u << 19;
 constexpr uint32_t CTL_MASK = 0xffff0000u;
 
 // decide early exit / bbox need after the duplicate filter (polytope.py:1113-1118)
@@ -716,6 +769,8 @@ int pb200_normalize_batch(const double* A, const double* b, const int32_t* m_row
     return launch_normalize(A, b, m_rows, P, m, d, 1, An, bn, valid, (cudaStream_t)stream);
 }
 
+void pb200_lane_solver(int on) { g_lane_enabled = on != 0; }
+
 void pb200_normalize_variant(int variant) { g_norm_variant = variant < -2 || variant > 2 ? -2 : variant; }
 
 int pb200_cheby_batch(const double* A, const double* b, const int32_t* m_rows, const uint64_t* rows, int P, int m,
@@ -735,8 +790,14 @@ int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows, in
     if (P == 0) return PB200_OK;
     // the LP kernel writes the raw optimised coordinates into lo / hi, the
     // resolve kernel then applies the reference's status conventions in place
-    BboxLP prob{A, b, m_rows, nullptr, nullptr, 0, m, d, 0, lo, hi, status, nullptr};
-    int rc = launch_lp(prob, (long long)P * 2 * d, m, d, (cudaStream_t)stream);
+    int rc;
+    if (lane_applies(m, d)) {
+        BboxLanes prob{A, b, m_rows, nullptr, nullptr, 0, 0, m, d, 0, lo, hi, status, nullptr};
+        rc = launch_lanes(prob, P, m, (cudaStream_t)stream);
+    } else {
+        BboxLP prob{A, b, m_rows, nullptr, nullptr, 0, m, d, 0, lo, hi, status, nullptr};
+        rc = launch_lp(prob, (long long)P * 2 * d, m, d, (cudaStream_t)stream);
+    }
     if (rc) return rc;
     bbox_resolve_kernel<<<blocks_for((long long)P * d, 256), 256, 0, (cudaStream_t)stream>>>(status, A, b, m_rows, P, m, d, lo, hi);
     ++g_launches;
@@ -791,8 +852,17 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     }
     stage_mark(3, st);
     // 4. bounding box of Polytope(A_arr, b_arr) where neq > 3 nx
-    BboxLP bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
-    if ((rc = launch_lp(bb, (long long)P * 2 * d, m, d, st))) return rc;
+    if (lane_applies(m, d)) {
+        BboxLanes bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, CTL_RETRY_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
+        if ((rc = launch_lanes(bb, P, m, st))) return rc;
+        // safety net: polytopes with an LP the lane solver could not finish (none on the BASELINE
+        // workloads) go through the warp-per-LP kernel, whose arithmetic differs
+        BboxLP again{An, ws.bn, nullptr, ws.rows1, flags, CTL_RETRY_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
+        if ((rc = launch_lp(again, (long long)P * 2 * d, m, d, st))) return rc;
+    } else {
+        BboxLP bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
+        if ((rc = launch_lp(bb, (long long)P * 2 * d, m, d, st))) return rc;
+    }
     stage_mark(4, st);
     // 5. candidate filter
     candidate_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(An, ws.bn, ws.rows1, ws.bblo, ws.bbhi, ws.bbstatus,
@@ -802,8 +872,15 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     stage_mark(5, st);
     // 6. one LP per surviving row
     PB_CHECK_CUDA(cudaMemsetAsync(ws.keep_lp, 0, sizeof(uint64_t) * P, st));
-    RowLP row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, m, d, abs_tol, ws.keep_lp, lp_iters};
-    if ((rc = launch_lp(row, (long long)P * m, m, d, st))) return rc;
+    if (lane_applies(m, d)) {
+        RowLanes row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, CTL_RETRY_ROWS, m, d, abs_tol, ws.keep_lp, lp_iters};
+        if ((rc = launch_lanes(row, P, m, st))) return rc;
+        RowLP again{An, ws.bn, ws.rows2, flags, CTL_RETRY_ROWS, m, d, abs_tol, ws.keep_lp, lp_iters};
+        if ((rc = launch_lp(again, (long long)P * m, m, d, st))) return rc;
+    } else {
+        RowLP row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, m, d, abs_tol, ws.keep_lp, lp_iters};
+        if ((rc = launch_lp(row, (long long)P * m, m, d, st))) return rc;
+    }
     stage_mark(6, st);
     // 7. results
     finalize_kernel<<<blocks_for((long long)P * 32, 256), 256, 0, st>>>(ws.bn, ws.rows2, ws.keep_lp, flags, P, m, d, keep,

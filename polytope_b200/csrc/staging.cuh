@@ -110,4 +110,52 @@ __device__ __forceinline__ void append_norm_column(const S& w, int cnt, int d, i
     __syncwarp();
 }
 
+// lpsolve() callers floor()/ceil() coordinates of optimal vertices (enumerate_integral_points,
+// polytope.py:2352-2358, pinned by the reference's test_enumerate_integral_points): a simplex
+// returns x_j = h_i / G_ij without rounding error when an active row has the single non-zero
+// entry G_ij.  The interior-point + polish solution sits within ~1e-16 of that; this snaps it:
+// a solution component within 1e-12 of such a row's h_i / G_ij becomes exactly that quotient
+// (lowest row wins).  x_own is the lane-owned component (lanes < n); vec is >= n doubles of scratch.
+template <int RPL, class S>
+__device__ __forceinline__ double snap_axis_rows(const S& w, double* vec, int m, int n, int lane,
+                                                 const double (&h)[RPL], double x_own) {
+    if (lane < n) vec[lane] = x_own;
+    __syncwarp();
+    int cj[RPL];
+    double cv[RPL];
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int i = lane + 32 * r;
+        cj[r] = -1;
+        cv[r] = 0.0;
+        if (i < m && h[r] < 1e300) {
+            int nz = 0, jj = 0;
+            double a = 1.0;
+            for (int j = 0; j < n; ++j) {
+                const double g = w.G[j * w.MP + i];
+                if (g != 0.0) { ++nz; jj = j; a = g; }
+            }
+            if (nz == 1) {
+                const double v = __ddiv_rn(h[r], a);
+                if (fabs(v - vec[jj]) <= 1e-12 * fmax(1.0, fabs(v))) { cj[r] = jj; cv[r] = v; }
+            }
+        }
+    }
+    double out = x_own;
+    for (int j = 0; j < n; ++j) {
+        bool found = false;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) {
+            const unsigned bal = __ballot_sync(FULL_MASK, !found && cj[r] == j);
+            if (bal) {
+                const double v = __shfl_sync(FULL_MASK, cv[r], __ffs(bal) - 1);
+                if (lane == j) out = v;
+                found = true;
+            }
+        }
+    }
+    __syncwarp();
+    return out;
+}
+
 }  // namespace pb200

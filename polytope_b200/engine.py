@@ -612,3 +612,13 @@ def profile_read():
 
 def launch_count():
     return int(_capi.lib().pb200_launch_count())
+
+
+def lane_solver(on=True):
+    """A/B switch: reduce / bounding-box LPs (d <= 8, m <= 64) on the one-LP-per-lane solver
+    (default) or on the warp-per-LP kernels."""
+    _capi.lib().pb200_lane_solver(int(bool(on)))
+
+
+if __import__('os').environ.get('PB200_LANE_SOLVER', '') == '0':
+    lane_solver(False)

@@ -87,7 +87,8 @@ def solve_lp(c, G, h, max_iter=MAX_ITER, polish=True, trace=None, early=True):
             relgap = np.inf
         if trace is not None:
             trace.append((it, pres, dres, gap, tau, kap, pcost))
-        if pres <= FEAS_TOL and dres <= FEAS_TOL and (gap <= GAP_TOL or relgap <= GAP_TOL):
+        if pres <= FEAS_TOL and ((dres <= FEAS_TOL and (gap <= GAP_TOL or relgap <= GAP_TOL))
+                                 or (dres <= 1e-6 and (gap <= 1e-13 or relgap <= 1e-13))):   # stalled dual residual
             status = 0
             break
         if (early and etol > 1e-7 and not lineal and pres <= etol and dres <= etol
@@ -102,8 +103,16 @@ def solve_lp(c, G, h, max_iter=MAX_ITER, polish=True, trace=None, early=True):
             status = 2
             break
         if cx < 0 and np.linalg.norm(G @ x + s) / (-cx) * nc / nh <= FEAS_TOL * 1e1 and tau < 1e-3 * kap:
-            status = 3
-            break
+            # unbounded if feasible at all: HiGHS reports 2 for an LP that is infeasible as well,
+            # so the feasibility problem (c = 0) is solved first, from the start point
+            lineal = True
+            c = np.zeros(n)
+            nc = 1.0
+            x = np.zeros(n)
+            s = np.maximum(h, 0) + 1.0
+            z = np.ones(m)
+            tau, kap = 1.0, 1.0
+            continue
         if it == max_iter:
             break
         d = z / s
