@@ -40,9 +40,9 @@ struct LaneData {
         for (int j = 0; j < LANE_NS / 2; ++j) { const double2 v = p[j]; g[2 * j] = v.x; g[2 * j + 1] = v.y; }
     }
     __device__ __forceinline__ double h(int i) const {
-        const double a = hA[i];
-        if (k < 0) return a;
-        return i < k ? hB[i] : (i == k ? __dadd_rn(a, 0.1) : a);
+        const double* src = i < k ? hB : hA;          // rows before k carry the +0.1 / -0.1 round trip
+        const double a = src[i];
+        return i == k ? __dadd_rn(a, 0.1) : a;
     }
     __device__ __forceinline__ double c(int j) const { return cj < 0 ? -G[k * LANE_NS + j] : (j == cj ? cs : 0.0); }
     __device__ __forceinline__ double& s(int i) { return sz[(2 * i) * 32]; }
@@ -76,8 +76,9 @@ __device__ __forceinline__ void lane_renormalize(double* G, double* hA, int cnt,
             for (int j = 0; j < d; ++j) row[j] = __dmul_rn(row[j], mult);
             hA[i] = __dmul_rn(hA[i], mult);
         } else {
+            // the constructor drops the row (:130): staged as 0'x <= 1, which never binds
             for (int j = 0; j < d; ++j) row[j] = 0.0;
-            hA[i] = 1e308 * 10.0;          // +inf: the solver treats the row as absent
+            hA[i] = 1.0;
         }
     }
     __syncwarp();

@@ -154,12 +154,25 @@ PBL_FN double dotn(const double (&a)[NS], const double (&b)[NS]) {
 // The data accessor D of a lane provides
 //   int rows()                       rows of this lane's LP
 //   void row(int i, double (&g)[NS]) row i of G (zero-padded to NS columns)
-//   double h(int i)                  right-hand side (>= 1e300: the row does not exist)
+//   double h(int i)                  right-hand side, finite (an absent row is staged as 0'x <= 1)
 //   double c(int j)                  objective
 //   double& s(int i), double& z(int i)   the lane's slack / multiplier iterates
 //
 // lane_solve: the LP of this lane (has_lp == false: the lane idles through the collectives).
 // n = live columns (<= NS).
+//
+// Per iteration the rows are walked five times (A: residuals + normal matrix + right-hand sides,
+// B: affine step length, C: corrector right-hand side, D: step length, E: step); every pass
+// recomputes what it needs of a row from (g_i, h_i, s_i, z_i) and a few n-vectors, so the only
+// per-row state is (s_i, z_i).  The sums h'z_k of the KKT solutions come from n-vector dot
+// products (h'D G x = (G'D h)'x) instead of further passes.
+#ifndef PB200_LANE_UNROLL
+#define PB200_LANE_UNROLL 2
+#endif
+#define PBL_STR2(x) #x
+#define PBL_STR(x) PBL_STR2(x)
+#define PBL_ROWS _Pragma(PBL_STR(unroll PB200_LANE_UNROLL))
+
 template <int NS, class D, class W>
 PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
     constexpr int NT = NS * (NS + 1) / 2;
@@ -169,32 +182,27 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
     for (int j = 0; j < NS; ++j) res.x[j] = 0.0;
 
     // ---- start point (Mehrotra-style, as lp_warp_small.cuh) ----
-    int mlive = 0;
     double hh = 0.0, hmax = 0.0;
     for (int i = 0; i < m; ++i) {
-        double h = dat.h(i);
-        const bool live = h < 1e300;
-        h = live ? h : 0.0;
-        dat.s(i) = live ? fmax(h, 0.0) + 1.0 : 1.0;
-        dat.z(i) = live ? 1.0 : 0.0;
-        mlive += live ? 1 : 0;
+        const double h = dat.h(i);
+        dat.s(i) = fmax(h, 0.0) + 1.0;
+        dat.z(i) = 1.0;
         hh = fma(h, h, hh);
         hmax = fmax(hmax, fabs(h));
     }
-    double c0[NS], cz[NS], x[NS];
+    double c0[NS], x[NS];
     double cc2 = 0.0;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
         c0[j] = has_lp && j < n ? dat.c(j) : 0.0;
-        cz[j] = c0[j];
         x[j] = 0.0;
         cc2 = fma(c0[j], c0[j], cc2);
     }
     const double nh2 = fmax(1.0, hh);
     double nc2 = fmax(1.0, cc2);
-    const double rmu = 1.0 / (double)(mlive + 1);
+    const double rmu = 1.0 / (double)(m + 1);
     double tau = 1.0, kap = 1.0;
-    bool lineal = false, ready = false;
+    bool lineal = false, ready = false;     // lineal: the objective has been dropped (feasibility problem, c = 0)
     double etol = EARLY_TOL;
     int phase = has_lp ? PH_IPM : PH_DONE, it = 0, waited = 0;
 
@@ -203,6 +211,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
         // ================= one interior-point iteration =================
         if (W::any(phase == PH_IPM)) {
             if (phase == PH_IPM) {
+                const double csel = lineal ? 0.0 : 1.0;       // effective objective = csel * c0
                 // ---- pass A: residuals, normal matrix M = G'DG and G'[z | D h | D q_aff] ----
                 double M[NT], v1[NS], v2[NS], v3[NS];
 #pragma unroll
@@ -210,17 +219,16 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                 for (int j = 0; j < NS; ++j) { v1[j] = 0.0; v2[j] = 0.0; v3[j] = 0.0; }
                 double sz = 0.0, hz = 0.0, rz2 = 0.0, gxs2 = 0.0, dhh = 0.0, dhq = 0.0;
+                PBL_ROWS
                 for (int i = 0; i < m; ++i) {
                     double g[NS];
                     dat.row(i, g);
-                    double h = dat.h(i);
-                    const bool live = h < 1e300;
-                    h = live ? h : 0.0;
+                    const double h = dat.h(i);
                     const double s = dat.s(i), z = dat.z(i);
                     const double gx = dotn<NS>(g, x);
                     const double d = z * rcp(s);
-                    const double rz = live ? gx + s - h * tau : 0.0;
-                    const double gxs = live ? gx + s : 0.0;
+                    const double gxs = gx + s;
+                    const double rz = gxs - h * tau;
                     sz = fma(s, z, sz);
                     hz = fma(h, z, hz);
                     rz2 = fma(rz, rz, rz2);
@@ -240,10 +248,13 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                 }
                 res.iters = it;
                 double rxl[NS];
-                double rx2 = 0.0;
+                double rx2 = 0.0, cx = 0.0;
 #pragma unroll
-                for (int j = 0; j < NS; ++j) { rxl[j] = fma(cz[j], tau, v1[j]); rx2 = fma(rxl[j], rxl[j], rx2); }
-                const double cx = dotn<NS>(cz, x);
+                for (int j = 0; j < NS; ++j) {
+                    rxl[j] = fma(csel * c0[j], tau, v1[j]);
+                    rx2 = fma(rxl[j], rxl[j], rx2);
+                    cx = fma(csel * c0[j], x[j], cx);
+                }
                 const double rt = cx + hz + kap;
                 const double mu = (sz + tau * kap) * rmu;
                 const double tinv = rcp(tau);
@@ -288,12 +299,10 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                                 tau = 1.0;
                                 kap = 1.0;
 #pragma unroll
-                                for (int j = 0; j < NS; ++j) { cz[j] = 0.0; x[j] = 0.0; }
+                                for (int j = 0; j < NS; ++j) x[j] = 0.0;
                                 for (int i = 0; i < m; ++i) {
-                                    const double h = dat.h(i);
-                                    const bool live = h < 1e300;
-                                    dat.s(i) = live ? fmax(h, 0.0) + 1.0 : 1.0;
-                                    dat.z(i) = live ? 1.0 : 0.0;
+                                    dat.s(i) = fmax(dat.h(i), 0.0) + 1.0;
+                                    dat.z(i) = 1.0;
                                 }
                                 if (it == 0) it = 1;
                             }
@@ -309,7 +318,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                         // whenever it is feasible -> continue with c = 0 and report 3 instead of 0
                         double uu[NS], back[NS];
 #pragma unroll
-                        for (int j = 0; j < NS; ++j) { uu[j] = cz[j]; back[j] = 0.0; }
+                        for (int j = 0; j < NS; ++j) { uu[j] = c0[j]; back[j] = 0.0; }
                         chol_solve<NS>(M, uu);
                         for (int i = 0; i < m; ++i) {
                             double g[NS];
@@ -321,11 +330,9 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                         }
                         double rmax = 0.0, cmax = 0.0;
 #pragma unroll
-                        for (int j = 0; j < NS; ++j) { rmax = fmax(rmax, fabs(cz[j] - back[j])); cmax = fmax(cmax, fabs(cz[j])); }
+                        for (int j = 0; j < NS; ++j) { rmax = fmax(rmax, fabs(c0[j] - back[j])); cmax = fmax(cmax, fabs(c0[j])); }
                         if (rmax > 1e-9 * fmax(cmax, 1e-300)) {
                             lineal = true;
-#pragma unroll
-                            for (int j = 0; j < NS; ++j) cz[j] = 0.0;
                             nc2 = 1.0;
                             it = 1;
                             restart = true;
@@ -334,39 +341,37 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                 }
                 if (phase == PH_IPM && !restart) {
                     // ---- predictor: K [x1; z1] = [-c; h],  K [x2; z2] = [-rx; q_aff] ----
-                    double X1[NS], X2[NS];
+                    double X1[NS], xa[NS];
 #pragma unroll
-                    for (int j = 0; j < NS; ++j) { X1[j] = v2[j] - cz[j]; X2[j] = v3[j] - rxl[j]; }
+                    for (int j = 0; j < NS; ++j) { X1[j] = fma(-csel, c0[j], v2[j]); xa[j] = v3[j] - rxl[j]; }
                     chol_solve<NS>(M, X1);
-                    chol_solve<NS>(M, X2);
-                    const double cx1 = dotn<NS>(cz, X1), cx2 = dotn<NS>(cz, X2);
+                    chol_solve<NS>(M, xa);
+                    double cx1 = 0.0, cx2 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) { cx1 = fma(csel * c0[j], X1[j], cx1); cx2 = fma(csel * c0[j], xa[j], cx2); }
                     // h'z1 and h'z2 of the two KKT solutions z_k = D (G x_k - q_k) without a pass over the
                     // rows: h'D G x_k = v2'x_k, and h'D h, h'D q_aff were accumulated in pass A
                     const double hz1 = dotn<NS>(v2, X1) - dhh;
-                    const double hz2 = dotn<NS>(v2, X2) - dhq;
+                    const double hz2 = dotn<NS>(v2, xa) - dhq;
                     const double kot = kap * tinv;
                     const double den = cx1 + hz1 - kot;                            // < 0
                     const double rden = rcp(den);
                     const double dta = (-rt + kap - cx2 - hz2) * rden;
                     const double dka = -kap - kot * dta;
                     const double kinv = rcp(kap);
-                    double xa[NS];                                                 // affine direction in x (without dtau part: x2 + dta x1)
+                    // affine direction in x (without its dtau part): x2 + dta x1
 #pragma unroll
-                    for (int j = 0; j < NS; ++j) xa[j] = fma(dta, X1[j], X2[j]);
+                    for (int j = 0; j < NS; ++j) xa[j] = fma(dta, X1[j], xa[j]);
                     double ratio = fmax(fmax(-dta * tinv, -dka * kinv), 0.0);
-                    for (int i = 0; i < m; ++i) {            // pass B2: affine step length
+                    PBL_ROWS
+                    for (int i = 0; i < m; ++i) {            // pass B: affine step length
                         double g[NS];
                         dat.row(i, g);
-                        double h = dat.h(i);
-                        const bool live = h < 1e300;
-                        if (!live) continue;
-                        const double s = dat.s(i), z = dat.z(i);
-                        const double sinv = rcp(s), zinv = rcp(z);
-                        const double d = z * sinv;
+                        const double h = dat.h(i);
                         const double q = h * tau - dotn<NS>(g, x);
-                        const double dza = d * (dotn<NS>(g, xa) - q - dta * h);
-                        const double dsa = -s - s * zinv * dza;
-                        ratio = fmax(ratio, fmax(-dsa * sinv, -dza * zinv));
+                        // w = dza / z;  -dsa / s = 1 + w
+                        const double w = rcp(dat.s(i)) * (dotn<NS>(g, xa) - q - dta * h);
+                        ratio = fmax(ratio, fmax(1.0 + w, -w));
                     }
                     const double alpha_aff = ratio > 1.0 ? rcp(ratio) : 1.0;
                     const double om = 1.0 - alpha_aff;
@@ -378,14 +383,14 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                     double dhqc = 0.0;
 #pragma unroll
                     for (int j = 0; j < NS; ++j) X3[j] = 0.0;
+                    PBL_ROWS
                     for (int i = 0; i < m; ++i) {
                         double g[NS];
                         dat.row(i, g);
-                        double h = dat.h(i);
-                        const bool live = h < 1e300;
-                        if (!live) continue;
+                        const double h = dat.h(i);
                         const double s = dat.s(i), z = dat.z(i);
-                        const double sinv = rcp(s), zinv = rcp(z);
+                        const double isz = rcp(s * z);
+                        const double sinv = isz * z, zinv = isz * s;
                         const double d = z * sinv;
                         const double q = h * tau - dotn<NS>(g, x);
                         const double rz = s - q;
@@ -401,23 +406,26 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                     for (int j = 0; j < NS; ++j) X3[j] = fma(-eta, rxl[j], X3[j]);
                     chol_solve<NS>(M, X3);
-                    const double cx3 = dotn<NS>(cz, X3);
-                    const double hz3 = dotn<NS>(v2, X3) - dhqc;      // h'D (G x3 - q_cor), as above
+                    const double v2x3 = dotn<NS>(v2, X3);
+                    double cx3 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) cx3 = fma(csel * c0[j], X3[j], cx3);
+                    const double hz3 = v2x3 - dhqc;                   // h'D (G x3 - q_cor), as above
                     const double bk = -tau * kap + sm - dta * dka;
                     const double dtau = (-eta * rt - bk * tinv - cx3 - hz3) * rden;
                     const double dkap = (bk - kap * dtau) * tinv;
-                    double xf[NS];                                                 // final direction in x
+                    // final direction in x: x3 + dtau x1
 #pragma unroll
-                    for (int j = 0; j < NS; ++j) xf[j] = fma(dtau, X1[j], X3[j]);
+                    for (int j = 0; j < NS; ++j) X3[j] = fma(dtau, X1[j], X3[j]);
                     ratio = fmax(fmax(-dtau * tinv, -dkap * kinv), 0.0);
-                    for (int i = 0; i < m; ++i) {            // pass D2: step length
+                    PBL_ROWS
+                    for (int i = 0; i < m; ++i) {            // pass D: step length
                         double g[NS];
                         dat.row(i, g);
-                        double h = dat.h(i);
-                        const bool live = h < 1e300;
-                        if (!live) continue;
+                        const double h = dat.h(i);
                         const double s = dat.s(i), z = dat.z(i);
-                        const double sinv = rcp(s), zinv = rcp(z);
+                        const double isz = rcp(s * z);
+                        const double sinv = isz * z, zinv = isz * s;
                         const double d = z * sinv;
                         const double q = h * tau - dotn<NS>(g, x);
                         const double rz = s - q;
@@ -425,20 +433,20 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                         const double dsa = -s - s * zinv * dza;
                         const double bs = -s * z + sm - dsa * dza;
                         const double qc = -eta * rz - bs * zinv;
-                        const double dz = d * (dotn<NS>(g, xf) - qc - dtau * h);
+                        const double dz = d * (dotn<NS>(g, X3) - qc - dtau * h);
                         const double ds = (bs - s * dz) * zinv;
                         ratio = fmax(ratio, fmax(-ds * sinv, -dz * zinv));
                     }
                     const double amax = ratio > 0.0 ? rcp(ratio) : 1e30;
                     const double alpha = fmin(1.0, STEP * amax);
+                    PBL_ROWS
                     for (int i = 0; i < m; ++i) {            // pass E: take the step in (s, z)
                         double g[NS];
                         dat.row(i, g);
-                        double h = dat.h(i);
-                        const bool live = h < 1e300;
-                        if (!live) continue;
+                        const double h = dat.h(i);
                         const double s = dat.s(i), z = dat.z(i);
-                        const double sinv = rcp(s), zinv = rcp(z);
+                        const double isz = rcp(s * z);
+                        const double sinv = isz * z, zinv = isz * s;
                         const double d = z * sinv;
                         const double q = h * tau - dotn<NS>(g, x);
                         const double rz = s - q;
@@ -446,13 +454,13 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                         const double dsa = -s - s * zinv * dza;
                         const double bs = -s * z + sm - dsa * dza;
                         const double qc = -eta * rz - bs * zinv;
-                        const double dz = d * (dotn<NS>(g, xf) - qc - dtau * h);
+                        const double dz = d * (dotn<NS>(g, X3) - qc - dtau * h);
                         const double ds = (bs - s * dz) * zinv;
                         dat.s(i) = fma(alpha, ds, s);
                         dat.z(i) = fma(alpha, dz, z);
                     }
 #pragma unroll
-                    for (int j = 0; j < NS; ++j) x[j] = fma(alpha, xf[j], x[j]);
+                    for (int j = 0; j < NS; ++j) x[j] = fma(alpha, X3[j], x[j]);
                     tau = fma(alpha, dtau, tau);
                     kap = fma(alpha, dkap, kap);
                     ++it;
@@ -476,7 +484,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
             for (int j = 0; j < NS; ++j) xp[j] = x[j] * te;
             // rows with z > s are taken as the optimal face
             int nact = 0;
-            for (int i = 0; i < m; ++i) nact += (dat.h(i) < 1e300 && dat.z(i) > dat.s(i)) ? 1 : 0;
+            for (int i = 0; i < m; ++i) nact += dat.z(i) > dat.s(i) ? 1 : 0;
             double f0 = 0.0;
             if (!early) {
                 f0 = dotn<NS>(c0, xp);
@@ -491,7 +499,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                 for (int e = 0; e < NT; ++e) M[e] = 0.0;
                 for (int i = 0; i < m; ++i) {
-                    if (!(dat.h(i) < 1e300 && dat.z(i) > dat.s(i))) continue;
+                    if (!(dat.z(i) > dat.s(i))) continue;
                     double g[NS];
                     dat.row(i, g);
 #pragma unroll
@@ -514,12 +522,11 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                     for (int j = 0; j < NS; ++j) { vp[j] = 0.0; vd[j] = 0.0; }
                     double ft = 0.0, fslack = -1e300, fymin = -1e300, fymax = 0.0;
+                    PBL_ROWS
                     for (int i = 0; i < m; ++i) {
-                        const double h = dat.h(i);
-                        if (!(h < 1e300)) continue;
                         double g[NS];
                         dat.row(i, g);
-                        const double rr = h - dotn<NS>(g, xp);
+                        const double rr = dat.h(i) - dotn<NS>(g, xp);
                         fslack = fmax(fslack, -rr);
                         const double z = dat.z(i);
                         if (z > dat.s(i)) {
