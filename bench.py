@@ -7,28 +7,33 @@ A step is one pass of the hot path over one batch: `reduce(Polytope(A, b))` for
 BASELINE.json configs[1] -- 10 000 random H-polytopes, d = 8, m = 32 (generator
 "box+cuts") -- per GPU.  An "LP" is one lpsolve-equivalent solve
 the reference algorithm needs on that input (counted by the kernels exactly as
-the oracle's call counter counts them; tests pin the equality).
+the reference's own lpsolve call counter counts them; tests pin the equality).
 
 Printed JSON (one line, rank 0):
   value     whole-job LPs/s with the batch resident in HBM (device-timed)
   e2e       same metric through the public host-buffer API: pinned host (A, b)
-            -> H2D -> pipeline -> D2H of masks/flags/counts, every step
-  roofline  the dominant kernel (row LPs): algorithmic bytes / its mean device
-            time (CUDA events on the launch stream inside the library) against
-            the measured HBM peak, plus the fp64 view that actually bounds it
-            and `ab_read`: the batched (A|b) read in isolation (the constructor-
-            normalisation kernel, bulk async copies) at the bench batch and on a
-            50x larger batch that streams from HBM (untimed extra, N = 1 ... rank 0)
-  cpu_baseline  the oracle port (scipy/HiGHS, as the reference calls it) on a
-            bounded sample of the same workload, all host cores (N = 1 only)
+            -> H2D -> pipeline -> (N > 1: one NCCL all-gather on the device) -> one D2H
+            of masks/flags/counts, every step
+  roofline  the dominant kernel (the row LPs of reduce): algorithmic bytes / its mean
+            device time (CUDA events on the launch stream inside the library) against
+            the measured HBM peak, plus the fp64 view that actually bounds it (peak
+            measured in this run by the library's DFMA kernel) and `ab_read`: the
+            batched (A|b) read in isolation (constructor normalisation, bulk async copies)
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, installed by oracle/make_ref.sh;
+            scipy/HiGHS path) on a bounded sample of the same workload, all host cores
+            (N = 1 only); kind "port" = the oracle restatement when oracle/_ref is absent
+  config.strong  strong scaling of the two BASELINE configs that ask for it: cfg5
+            (1 047 552 ordered-pair is_adjacent LPs, compute_adj semantics) and cfg4
+            (extreme() of 1 000 polytopes d = 12, m = 64), the units split over the N
+            ranks with their one all-gather, device-timed, max over ranks
 
 N > 1: launched by torchrun, one rank per GPU, weak scaling (each rank reduces
 its own 10 000 polytopes), one NCCL all-gather of the 64-bit keep masks per
 step; time = max over ranks.
 
---impl reference times the reference's CPU path (the oracle port: the
-reference is pure Python over scipy; /root/reference does not travel to the GPU
-box) on a bounded sample per step, with every host core.
+--impl reference times the reference's own CPU implementation of the path
+(`polytope.reduce(polytope.Polytope(A, b))` of oracle/_ref with its lpsolve calls
+counted) on a bounded sample per step, with every host core.
 """
 import argparse
 import json
@@ -60,10 +65,23 @@ def ipm_flops_per_iteration(m, n):
 
 
 # --------------------------------------------------------------------------
-# CPU arm: the oracle port, all host cores
+# CPU arm: the unmodified reference (or, without oracle/_ref, the oracle port), all host cores
 # --------------------------------------------------------------------------
+def reference_kind():
+    from oracle import ref_loader
+    return 'reference' if ref_loader.available() else 'port'
+
+
 def _cpu_chunk(args):
-    first, count = args
+    first, count, kind = args
+    if kind == 'reference':
+        from oracle import ref_loader
+        pc = ref_loader.load()
+        with ref_loader.count_lps() as n:
+            for i in range(first, first + count):
+                A, b = wl.box_cuts(1000 * CFG['cfg'] + i, CFG['m'], CFG['d'])
+                pc.reduce(pc.Polytope(A, b))
+        return n[0]
     from oracle import polytope_oracle as orc
     n = 0
     for i in range(first, first + count):
@@ -72,18 +90,28 @@ def _cpu_chunk(args):
     return n
 
 
-def cpu_reduce_sample(n_poly, cores, first=0):
-    """Oracle reduce() on `n_poly` polytopes of the workload; -> (LPs, seconds)."""
+def cpu_reduce_sample(n_poly, cores, first=0, kind='reference'):
+    """reduce() on `n_poly` polytopes of the workload on the host; -> (LPs, seconds)."""
+    import logging
     import multiprocessing as mp
+    logging.disable(logging.WARNING)                     # the reference warns about cvxopt at import
     per = max(1, n_poly // (cores * 4))
-    chunks = [(first + s, min(per, n_poly - s)) for s in range(0, n_poly, per)]
+    chunks = [(first + s, min(per, n_poly - s), kind) for s in range(0, n_poly, per)]
     ctx = mp.get_context('fork')
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_chunk, [(0, 1)] * cores)          # warm the workers (imports)
+        pool.map(_cpu_chunk, [(0, 1, kind)] * cores)     # warm the workers (imports)
         t0 = time.perf_counter()
         lps = sum(pool.map(_cpu_chunk, chunks))
         dt = time.perf_counter() - t0
+    logging.disable(logging.NOTSET)
     return lps, dt
+
+
+def _baseline_text(kind, sample, lps, secs=None):
+    what = ('the unmodified reference (oracle/_ref: polytope.reduce(polytope.Polytope(A, b)), its lpsolve calls '
+            'counted)' if kind == 'reference' else 'oracle port of the reference reduce()')
+    return '%d polytopes of cfg2 (%d LPs%s): %s over scipy.optimize.linprog/HiGHS, multiprocessing over all host ' \
+           'cores' % (sample, lps, '' if secs is None else ', %.1f s wall' % secs, what)
 
 
 def run_reference(args):
@@ -91,12 +119,13 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
+    kind = reference_kind()
     sample = 16 * cores                                  # ~25 CPU-seconds per step
     for _ in range(args.warmup):
-        cpu_reduce_sample(cores, cores)
+        cpu_reduce_sample(cores, cores, kind=kind)
     lps, secs = 0, 0.0
     for k in range(args.steps):
-        a, b = cpu_reduce_sample(sample, cores, first=k * sample)
+        a, b = cpu_reduce_sample(sample, cores, first=k * sample, kind=kind)
         lps += a
         secs += b
     value = lps / secs
@@ -105,10 +134,8 @@ def run_reference(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample_polytopes_per_step': sample},
-        'cpu_baseline': {'value': value, 'unit': 'LPs/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d polytopes of cfg2 per step (%d LPs total), oracle port of the reference '
-                                   'reduce() over scipy.optimize.linprog/HiGHS, multiprocessing over all host '
-                                   'cores' % (sample, lps)},
+        'cpu_baseline': {'value': value, 'unit': 'LPs/s', 'cores': cores, 'kind': kind,
+                         'sample': _baseline_text(kind, sample, lps) + ', per step'},
         'e2e': {'value': value, 'unit': 'LPs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -161,6 +188,22 @@ class ClockSampler(object):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def measured_traffic():
+    """ncu DRAM bytes per launch of the dominant kernel, only if the capture belongs to the
+    sources the loaded library was built from (tools/update_traffic.py records the digest)."""
+    path = os.path.join(ROOT, 'profiles', 'row_lp_dram_bytes.json')
+    stamp = os.path.join(ROOT, 'polytope_b200', 'libpolytope_b200.so.srchash')
+    try:
+        doc = json.load(open(path))
+        built = open(stamp).read().strip()
+    except (OSError, ValueError):
+        return None, 'no ncu capture recorded for this build (profiles/row_lp_dram_bytes.json or the .srchash is missing)'
+    if doc.get('srchash') != built:
+        return None, 'stale: profiles/row_lp_dram_bytes.json was captured on source digest %s, the library is %s' % (
+            str(doc.get('srchash'))[:12], built[:12])
+    return doc.get('dram_bytes_per_launch'), doc.get('source')
+
+
 # --------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------
@@ -174,12 +217,11 @@ def run_gpu(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
+        kind = reference_kind()
         sample = 16 * cores
-        lps, secs = cpu_reduce_sample(sample, cores)
-        cpu_baseline = {'value': lps / secs, 'unit': 'LPs/s', 'cores': cores, 'kind': 'port',
-                        'sample': '%d polytopes of cfg2 (%d LPs, %.1f s wall): oracle port of the reference '
-                                  'reduce() over scipy.optimize.linprog/HiGHS, multiprocessing over all host '
-                                  'cores' % (sample, lps, secs)}
+        lps, secs = cpu_reduce_sample(sample, cores, kind=kind)
+        cpu_baseline = {'value': lps / secs, 'unit': 'LPs/s', 'cores': cores, 'kind': kind,
+                        'sample': _baseline_text(kind, sample, lps, secs)}
 
     import torch
     import torch.distributed as dist
@@ -218,13 +260,18 @@ def run_gpu(args):
         return res, keep
 
     def step_e2e():
-        # the public host-buffer call: pinned (A, b) in, numpy masks / flags / counts out; the
-        # H2D and D2H copies happen inside (chunked over two streams, overlapping the kernels)
-        res = engine.reduce_batch(A_pin, b_pin, want_A=False, want_b=False)
-        keep = torch.from_numpy(res.keep)
-        if world > 1:
-            keep = sharding.allgather_blocks(keep.to('cuda'), world * P).cpu()
-        return keep, torch.from_numpy(res.flags), torch.from_numpy(res.n_lp), torch.from_numpy(res.lp_iters)
+        # the public host-buffer call: pinned (A, b) in, masks / flags / counts out.  N = 1: the H2D
+        # and D2H copies happen inside (chunked over two streams, overlapping the kernels), results
+        # are numpy arrays.  N > 1: results stay on the device for the one all-gather, then one D2H.
+        if world == 1:
+            res = engine.reduce_batch(A_pin, b_pin, want_A=False, want_b=False)
+            return (torch.from_numpy(res.keep), torch.from_numpy(res.flags), torch.from_numpy(res.n_lp),
+                    torch.from_numpy(res.lp_iters))
+        res = engine.reduce_batch(A_pin.to('cuda', non_blocking=True), b_pin.to('cuda', non_blocking=True), want_A=False)
+        packed = torch.stack([res.keep, res.flags.to(torch.int64), res.n_lp.to(torch.int64),
+                              res.lp_iters.to(torch.int64)], 1)
+        allp = sharding.allgather_blocks(packed, world * P).cpu()
+        return allp[:, 0], allp[:, 1], allp[:, 2], allp[:, 3]
 
     def timed(step, steps, profile=False):
         """K steps, each bracketed by its own CUDA events on the launch stream,
@@ -274,6 +321,9 @@ def run_gpu(args):
         ms_dev, ms_e2e, lps_all = tmax[0].item(), tmax[1].item(), tsum[2].item()
     else:
         lps_all = float(lps_step)
+
+    strong = None if args.no_strong else strong_scaling(torch, dist, engine, sharding, rank, world, barrier)
+    dfma_peak = engine.measure_dfma_tflops() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -289,7 +339,8 @@ def run_gpu(args):
     row_iters = iters_step * kept_rows / max(lps_step, 1)
     flops = row_iters * ipm_flops_per_iteration(int(round(kept_rows / P)), d)
     h2d = A_pin.numel() * 8 + b_pin.numel() * 8
-    d2h = sum(x.numel() * x.element_size() for x in e2e_out)
+    d2h = sum(x.numel() * x.element_size() for x in e2e_out)          # what one rank copies back
+    traffic, traffic_src = measured_traffic()
     line = {
         'metric': METRIC, 'value': value, 'unit': 'LPs/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True,
@@ -299,33 +350,81 @@ def run_gpu(args):
                    'mean_ipm_iterations_per_lp': iters_step / max(lps_step, 1),
                    'l2': 'flushed before every step (256 MiB memset, untimed); each step timed with its own '
                          'CUDA event pair on the launch stream',
-                   'collective': 'none' if world == 1 else 'one NCCL all_gather of int64 keep masks per step'},
+                   'collective': 'none' if world == 1 else 'one NCCL all_gather of int64 keep masks per step',
+                   'strong': strong},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'LPs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'roofline': {'bound': 'hbm', 'kernel': 'lp_kernel_small<1, RowLP> (reduce row LPs)', 'achieved': achieved,
-                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
+        'roofline': {'bound': 'hbm', 'kernel': 'lane_kernel<RowLanes> (reduce row LPs, one LP per lane)', 'achieved': achieved,
+                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
+                     'traffic_source': traffic_src,
                      'peak_source': peak_src, 'kernel_ms': row_ms, 'algorithmic_bytes': alg_bytes,
                      'kernel_share_of_step': row_ms / (ms_dev / args.steps),
                      'stage_ms': stages,
-                     'fp64': {'achieved_tflops': flops / (row_ms * 1e-3) / 1e12, 'peak_tflops': 35.45,
-                              'peak_source': 'DFMA microbenchmark on this pool (profiles/r01_microbench_fp64_shfl_lds.txt)',
-                              'frac': flops / (row_ms * 1e-3) / 1e12 / 35.45,
+                     'fp64': {'achieved_tflops': flops / (row_ms * 1e-3) / 1e12, 'peak_tflops': dfma_peak,
+                              'peak_source': 'measured in this run: pb200_measure_dfma_tflops (DFMA chains, 32 warps/SM, CUDA events)',
+                              'frac': flops / (row_ms * 1e-3) / 1e12 / dfma_peak,
                               'note': 'the path is fp64 latency/issue bound, not HBM bound (SURVEY.md 8d)'}},
         'cpu_baseline': cpu_baseline,
     }
     line['roofline']['ab_read'] = ab_read_roofline(P, m, d, stages.get('normalize'), hbm_peak)
-    traffic_file = os.path.join(ROOT, 'profiles', 'row_lp_dram_bytes.json')
-    if os.path.exists(traffic_file):
-        try:
-            line['roofline']['traffic'] = json.load(open(traffic_file)).get('dram_bytes_per_launch')
-        except (OSError, ValueError):
-            pass
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def strong_scaling(torch, dist, engine, sharding, rank, world, barrier, reps=5):
+    """The two BASELINE configs quoted as sharded over the GPUs of one box, total work fixed:
+    cfg5 (prop2partition adjacency grid, all ordered pairs as MetricPartition.compute_adj walks
+    them, prop2partition.py:253-261) and cfg4 (extreme() of 1 000 polytopes d = 12, m = 64).
+    Each rank does its contiguous block of pairs / polytopes; one all-gather of the flags, and of
+    the vertex counts + (ragged) vertices.  Device-timed with CUDA events, max over ranks."""
+    out = {}
+
+    def run(fn, reps):
+        fn()
+        fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            res = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), res
+
+    # cfg5
+    A, b, idx = wl.box_grid((32, 32))
+    n = len(A)
+    Ad, bd = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()     # unit rows: already constructor-normalised
+    ms, flags = run(lambda: sharding.adjacency_ordered_sharded(Ad, bd), reps)
+    pairs = n * (n - 1)
+    ii, jj = np.nonzero(~np.eye(n, dtype=bool))
+    touch = np.abs(idx[ii] - idx[jj]).max(1) <= 1
+    out['cfg5'] = {'workload': '32x32 grid of unit boxes, all %d ordered pairs (compute_adj), one is_adjacent LP (8x3) each, '
+                               'pair range split over %d GPU(s), one all-gather of the flags' % (pairs, world),
+                   'value': pairs / (ms * 1e-3), 'unit': 'LPs/s', 'ms': ms, 'scaling': 'strong',
+                   'flag_mismatches_vs_geometry': int((flags.cpu().numpy().astype(bool) != touch).sum())}
+    # cfg4
+    A4, b4 = wl.box_cuts_batch(4, 1000, 64, 12)
+    A4d, b4d = torch.from_numpy(A4).cuda(), torch.from_numpy(b4).cuda()
+    state = {'caps': None}
+
+    def cfg4():
+        counts, V, caps = sharding.extreme_tensor_sharded(A4d, b4d, caps=state['caps'])
+        state['caps'] = caps
+        return counts, V
+    ms, (counts, V) = run(cfg4, 3)
+    out['cfg4'] = {'workload': 'extreme() of 1000 box+cuts polytopes d=12 m=64 (reduce + cheby + polar dual + dual hull + '
+                               'vertices), polytopes split over %d GPU(s), all-gather of counts and vertices' % world,
+                   'value': 1000 / (ms * 1e-3), 'unit': 'polytopes/s', 'ms': ms, 'scaling': 'strong',
+                   'vertices': int(counts.sum().item()), 'vertices_per_s': float(counts.sum().item()) / (ms * 1e-3)}
+    return out
 
 
 def ab_read_roofline(P, m, d, stage_ms, hbm_peak, scale=50, reps=6):
@@ -374,6 +473,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='skip the cfg4 / cfg5 strong-scaling extras')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

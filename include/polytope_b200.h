@@ -125,6 +125,16 @@ int pb200_adjacent_pairs(const double* A, const double* b, int ncell, int mc, in
                          double abs_tol, uint8_t* adjacent, double* radius,
                          int8_t* status, void* stream);
 
+/* The same test over a contiguous range [t_begin, t_begin + T) of an implicit pair
+ * enumeration -- what a rank of a sharded partition job runs, no pair lists in memory:
+ *   order 0: t = i (i - 1) / 2 + j, j < i   (find_adjacent_regions, prop2partition.py:57-61)
+ *   order 1: all ordered pairs i != j, row-major over i  (MetricPartition.compute_adj,
+ *            prop2partition.py:253-261)
+ * Outputs are indexed from 0 (pair t_begin + k -> adjacent[k]). */
+int pb200_adjacent_range(const double* A, const double* b, int ncell, int mc, int d, int order,
+                         long long t_begin, long long T, double abs_tol, uint8_t* adjacent,
+                         double* radius, int8_t* status, void* stream);
+
 /* ---- point-set kernels ---------------------------- */
 
 /* contains(): which of N points (column vectors: points[d][N], exactly the
@@ -257,6 +267,11 @@ int pb200_profile_read(float* stage_ms, int n);
  * -1 = row-per-lane kernel without shared-memory staging.  All variants produce
  * identical bits; tools/normalize_bench.py measures them. */
 void pb200_normalize_variant(int variant);
+
+/* Measurement: fp64 FMA throughput of the current device in TFLOP/s (2 flop per DFMA), timed
+ * with CUDA events on `stream`; `scratch` is device memory of >= 1024 * #SMs doubles.  bench.py's
+ * roofline.fp64 divides by this instead of a datasheet figure. */
+int pb200_measure_dfma_tflops(double* scratch, size_t scratch_doubles, double* tflops, void* stream);
 
 /* Diagnostics: the reduce / bounding-box LPs of polytopes with d <= 8 and m <= 64 run on the
  * lane solver (one LP per lane, csrc/lp_lane.cuh); on = 0 sends them back to the warp-per-LP

@@ -29,6 +29,7 @@ SIGNATURES = {
     'pb200_profile_enable': (None, [c_int]),
     'pb200_normalize_variant': (None, [c_int]),
     'pb200_lane_solver': (None, [c_int]),
+    'pb200_measure_dfma_tflops': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     'pb200_profile_read': (c_int, [c_void_p, c_int]),
     'pb200_contains_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_longlong, c_double, c_int,
                                      c_void_p, c_void_p]),
@@ -45,6 +46,7 @@ SIGNATURES = {
                                 + [c_void_p]),
     'pb200_adjacent_pairs': (c_int, [c_void_p] * 2 + [c_int] * 3 + [c_void_p] * 2
                              + [c_longlong, c_double] + [c_void_p] * 4),
+    'pb200_adjacent_range': (c_int, [c_void_p] * 2 + [c_int] * 4 + [c_longlong, c_longlong, c_double] + [c_void_p] * 4),
 }
 
 

@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "staging.cuh"
+#include "normalize.cuh"      // bulk-copy / mbarrier wrappers
 #include "lp_lane.cuh"
 
 namespace pb200 {
@@ -20,9 +21,17 @@ constexpr int LANE_NG = 3;       // polytopes a warp holds per round
 #endif
 
 __host__ __device__ inline int lane_slot_doubles(int m) { return m * LANE_NS + 4; }   // +4: slots land in different banks
+// G[NG][slot] | hA[NG][m] | hB[NG][m] | sz[2 m][32] | raw[m NS + m] (landing zone of the bulk copies) | mbarrier
 __host__ __device__ inline size_t lane_smem_doubles(int m) {
-    return (size_t)LANE_NG * lane_slot_doubles(m) + 2 * LANE_NG * m + 64 * (size_t)m;
+    return (size_t)LANE_NG * lane_slot_doubles(m) + 2 * LANE_NG * m + 64 * (size_t)m + (size_t)m * LANE_NS + m + 2;
 }
+
+// per-warp staging context: where the TMA engine lands a polytope's (A, b) block
+struct LaneStage {
+    double* raw;
+    uint64_t* bar;
+    uint32_t parity;
+};
 
 // what a lane sees of its LP
 struct LaneData {
@@ -49,19 +58,43 @@ struct LaneData {
     __device__ __forceinline__ double& z(int i) { return sz[(2 * i + 1) * 32]; }
 };
 
-// rows selected by `mask` (ascending) of a row-major [m x d] matrix -> row-major [cnt][LANE_NS], zero padded
+// rows selected by `mask` (ascending) of a row-major [m x d] matrix -> row-major [cnt][LANE_NS], zero padded.
+// The polytope's (A, b) block is one contiguous span each: when the spans are 16-byte aligned they
+// are fetched by two 1-D bulk async copies (cp.async.bulk, the TMA engine; SASS UBLKCP) that
+// complete on the warp's mbarrier, and the rows are picked / padded out of shared memory;
+// otherwise by coalesced loads.
 __device__ __forceinline__ int lane_stage_masked(const double* __restrict__ Ap, const double* __restrict__ bp, int m, int d,
-                                                 uint64_t mask, double* G, double* hA, int lane) {
+                                                 uint64_t mask, double* G, double* hA, int lane, LaneStage& sg) {
     const int cnt = __popcll(mask);
+    const int total = m * d;
+    const bool bulk = (((uintptr_t)Ap | (uintptr_t)bp) & 15u) == 0 && (m & 1) == 0;
+    if (bulk) {
+        if (lane == 0) {
+            fence_smem_to_async_proxy();       // earlier reads of the landing zone are done (syncwarp of the previous use)
+            mbar_expect_tx(sg.bar, (uint32_t)((total + m) * sizeof(double)));
+            bulk_load(sg.raw, Ap, (uint32_t)(total * sizeof(double)), sg.bar);
+            bulk_load(sg.raw + total, bp, (uint32_t)(m * sizeof(double)), sg.bar);
+        }
+    }
     for (int e = lane; e < cnt * LANE_NS; e += 32) G[e] = 0.0;
     __syncwarp();
-    const int total = m * d;
-    for (int e = lane; e < total; e += 32) {
-        const int i = e / d, j = e - i * d;
-        if ((mask >> i) & 1ull) G[__popcll(mask & ((1ull << i) - 1ull)) * LANE_NS + j] = __ldg(Ap + e);
+    if (bulk) {
+        mbar_wait(sg.bar, sg.parity);
+        sg.parity ^= 1u;
+        for (int e = lane; e < total; e += 32) {
+            const int i = e / d, j = e - i * d;
+            if ((mask >> i) & 1ull) G[__popcll(mask & ((1ull << i) - 1ull)) * LANE_NS + j] = sg.raw[e];
+        }
+        for (int i = lane; i < m; i += 32)
+            if ((mask >> i) & 1ull) hA[__popcll(mask & ((1ull << i) - 1ull))] = sg.raw[total + i];
+    } else {
+        for (int e = lane; e < total; e += 32) {
+            const int i = e / d, j = e - i * d;
+            if ((mask >> i) & 1ull) G[__popcll(mask & ((1ull << i) - 1ull)) * LANE_NS + j] = __ldg(Ap + e);
+        }
+        for (int i = lane; i < m; i += 32)
+            if ((mask >> i) & 1ull) hA[__popcll(mask & ((1ull << i) - 1ull))] = __ldg(bp + i);
     }
-    for (int i = lane; i < m; i += 32)
-        if ((mask >> i) & 1ull) hA[__popcll(mask & ((1ull << i) - 1ull))] = __ldg(bp + i);
     __syncwarp();
     return cnt;
 }
@@ -100,8 +133,8 @@ struct RowLanes {
         if (!(flags[p] & run_mask)) return 0;
         return __popcll(rows[p] & low_bits(m));
     }
-    __device__ int stage(long long p, double* G, double* hA, double* hB, int lane) const {
-        const int cnt = lane_stage_masked(A + (size_t)p * m * d, b + (size_t)p * m, m, d, rows[p] & low_bits(m), G, hA, lane);
+    __device__ int stage(long long p, double* G, double* hA, double* hB, int lane, LaneStage& sg) const {
+        const int cnt = lane_stage_masked(A + (size_t)p * m * d, b + (size_t)p * m, m, d, rows[p] & low_bits(m), G, hA, lane, sg);
         for (int i = lane; i < cnt; i += 32) hB[i] = __dadd_rn(__dadd_rn(hA[i], 0.1), -0.1);
         __syncwarp();
         return cnt;
@@ -140,11 +173,11 @@ struct BboxLanes {
         if (need_flags && !(need_flags[p] & need_mask)) return 0;
         return 2 * d;
     }
-    __device__ int stage(long long p, double* G, double* hA, double* hB, int lane) const {
+    __device__ int stage(long long p, double* G, double* hA, double* hB, int lane, LaneStage& sg) const {
         uint64_t mask;
         if (rows) mask = rows[p] & low_bits(m);
         else mask = low_bits(m_rows ? min(max(m_rows[p], 0), m) : m);
-        const int cnt = lane_stage_masked(A + (size_t)p * m * d, b + (size_t)p * m, m, d, mask, G, hA, lane);
+        const int cnt = lane_stage_masked(A + (size_t)p * m * d, b + (size_t)p * m, m, d, mask, G, hA, lane, sg);
         if (renorm) lane_renormalize(G, hA, cnt, d, lane);
         return cnt;
     }
@@ -171,6 +204,12 @@ __global__ void __launch_bounds__(32, PB200_LANE_MINB) lane_kernel(const Prob pr
     double* hA = G + LANE_NG * GS;
     double* hB = hA + LANE_NG * m;
     double* sz = hB + LANE_NG * m;
+    LaneStage sg;
+    sg.raw = sz + 64 * (size_t)m;
+    sg.bar = reinterpret_cast<uint64_t*>(sg.raw + (size_t)m * LANE_NS + m + (m & 1));
+    sg.parity = 0;
+    if (lane == 0) mbar_init(sg.bar, 1);
+    __syncwarp();
     long long carry_p = -1;
     int carry_k = 0;
     for (;;) {
@@ -193,7 +232,7 @@ __global__ void __launch_bounds__(32, PB200_LANE_MINB) lane_kernel(const Prob pr
             }
             const int cnt = prob.count(p);
             if (cnt - k0 <= 0) continue;
-            const int rows = prob.stage(p, G + ns * GS, hA + ns * m, hB + ns * m, lane);
+            const int rows = prob.stage(p, G + ns * GS, hA + ns * m, hB + ns * m, lane, sg);
             const int take = min(cnt - k0, 32 - nl);
             if (lane >= nl && lane < nl + take) { my_p = p; my_k = k0 + lane - nl; my_slot = ns; my_rows = rows; }
             nl += take;
@@ -212,6 +251,208 @@ __global__ void __launch_bounds__(32, PB200_LANE_MINB) lane_kernel(const Prob pr
         lane::Result<LANE_NS> res;
         lane::lane_solve<LANE_NS, LaneData, lane::WarpLanes>(dat, my_p >= 0, prob.n(), res);
         if (my_p >= 0) prob.store(my_p, my_k, res);
+        __syncwarp();
+    }
+}
+
+
+// ------------------------------------------------------------------------
+// Independent small LPs (every LP has its own G): one LP per lane, the lane's rows in a
+// lane-interleaved shared-memory array (double2 granules: 128-bit loads, consecutive lanes on
+// consecutive granules, no bank conflicts).  Used when the LPs are small enough for a useful
+// number of resident warps: is_adjacent pairs of grid cells (prop2partition, cfg5: 8 x 3), the
+// Chebyshev LPs of is_fulldim / cheby_ball over a Region (cfg3: 16 x 7), envelope tests.
+// ------------------------------------------------------------------------
+template <int NS>
+struct OwnData {
+    double* G;      // this lane's granule column: element (i, j) at G[(i * (NS / 2) + (j >> 1)) * 64 + (j & 1)]
+    double* hv;     // hv[i * 32]
+    double* sz;
+    int m, cj;      // rows; objective = cs * e_cj
+    double cs;
+    __device__ __forceinline__ int rows() const { return m; }
+    __device__ __forceinline__ void row(int i, double (&g)[NS]) const {
+        const double2* p = reinterpret_cast<const double2*>(G) + i * (NS / 2) * 32;
+#pragma unroll
+        for (int j = 0; j < NS / 2; ++j) { const double2 v = p[j * 32]; g[2 * j] = v.x; g[2 * j + 1] = v.y; }
+    }
+    __device__ __forceinline__ void put_row(int i, const double (&g)[NS]) {
+        double2* p = reinterpret_cast<double2*>(G) + i * (NS / 2) * 32;
+#pragma unroll
+        for (int j = 0; j < NS / 2; ++j) p[j * 32] = make_double2(g[2 * j], g[2 * j + 1]);
+    }
+    __device__ __forceinline__ double h(int i) const { return hv[i * 32]; }
+    __device__ __forceinline__ double c(int j) const { return j == cj ? cs : 0.0; }
+    __device__ __forceinline__ double& s(int i) { return sz[(2 * i) * 32]; }
+    __device__ __forceinline__ double& z(int i) { return sz[(2 * i + 1) * 32]; }
+};
+
+template <int NS>
+__host__ __device__ inline size_t own_smem_doubles(int mr) { return (size_t)mr * 32 * (NS + 3); }
+
+// One constraint row of a Chebyshev LP, built the way the reference builds it: the Polytope
+// constructor's normalisation (polytope.py:128-138, rows with norm <= 1e-10 dropped -> staged as
+// 0'x <= 1) when `renorm`, then the norm column ||a_i|| of cheby_ball (polytope.py:1285-1286).
+// Sums of squares in numpy's order (d < 8: plain left-to-right).
+template <int NS>
+__device__ __forceinline__ void cheby_row(const double* __restrict__ a, double bi, int d, bool renorm, double (&g)[NS], double& h) {
+    double ss = 0.0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        g[j] = j < d ? __ldg(a + j) : 0.0;
+        if (j < d) ss = __dadd_rn(ss, __dmul_rn(g[j], g[j]));
+    }
+    h = bi;
+    if (renorm) {
+        const double nrm = sqrt(ss);
+        if (nrm > 1e-10) {
+            const double mult = __ddiv_rn(1.0, nrm);
+#pragma unroll
+            for (int j = 0; j < NS; ++j) g[j] = j < d ? __dmul_rn(g[j], mult) : 0.0;
+            h = __dmul_rn(bi, mult);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) g[j] = 0.0;
+            h = 1.0;
+        }
+        ss = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+            if (j < d) ss = __dadd_rn(ss, __dmul_rn(g[j], g[j]));
+    }
+    const double col = sqrt(ss);
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+        if (j == d) g[j] = col;
+}
+
+// is_adjacent, overlap=True (polytope.py:1856-1866): rows of both cells, b + tol, constructor
+// normalisation, Chebyshev LP, radius > tol/10.  Pairs from a list, or enumerated:
+// order 0: t = i(i-1)/2 + j, j < i (find_adjacent_regions, prop2partition.py:57-61);
+// order 1: all ordered pairs i != j, row-major (MetricPartition.compute_adj, :253-261).
+struct AdjacentOwn {
+    const double *A, *b;
+    int ncell, mc, d;
+    const int32_t *pi, *pj;
+    int order;
+    long long t_begin;
+    double abs_tol;
+    uint8_t* adjacent;
+    double* radius;
+    int8_t* status;
+    __device__ int n() const { return d + 1; }
+    __device__ void pair(long long t, int& i, int& j) const {
+        if (pi) { i = pi[t]; j = pj[t]; return; }
+        const long long u = t + t_begin;
+        if (order == 1) {
+            const long long ii = u / (ncell - 1);
+            const long long jj = u - ii * (ncell - 1);
+            i = (int)ii;
+            j = (int)(jj + (jj >= ii ? 1 : 0));
+            return;
+        }
+        long long ii = (long long)((1.0 + sqrt(1.0 + 8.0 * (double)u)) * 0.5);
+        while (ii * (ii - 1) / 2 > u) --ii;
+        while ((ii + 1) * ii / 2 <= u) ++ii;
+        i = (int)ii;
+        j = (int)(u - ii * (ii - 1) / 2);
+    }
+    template <int NS>
+    __device__ void stage(long long t, OwnData<NS>& dat) const {
+        int ci, cj;
+        pair(t, ci, cj);
+        dat.m = 2 * mc;
+        dat.cj = d;
+        dat.cs = -1.0;
+        for (int r = 0; r < 2 * mc; ++r) {
+            const int cell = r < mc ? ci : cj, i = r < mc ? r : r - mc;
+            double g[NS], h;
+            cheby_row<NS>(A + ((size_t)cell * mc + i) * d, __dadd_rn(__ldg(b + (size_t)cell * mc + i), abs_tol), d, true, g, h);
+            dat.put_row(r, g);
+            dat.hv[r * 32] = h;
+        }
+    }
+    template <int NS>
+    __device__ void store(long long t, const lane::Result<NS>& res) const {
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        double rr = nan;
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+            if (j == d && res.status == lane::OPTIMAL) rr = res.x[j];
+        adjacent[t] = (res.status == lane::OPTIMAL && rr > abs_tol / 10) ? 1 : 0;
+        if (radius) radius[t] = rr;
+        if (status) status[t] = (int8_t)res.status;
+    }
+};
+
+// cheby_ball of P stacked polytopes (polytope.py:1280-1300), rows used as given
+struct ChebyOwn {
+    const double *A, *b;
+    const int32_t* m_rows;
+    const uint64_t* rows;     // nullable row masks
+    int m, d;
+    double *r, *xc;
+    int8_t* status;
+    int32_t* lp_iters;        // nullable: = iterations of this LP
+    __device__ int n() const { return d + 1; }
+    template <int NS>
+    __device__ void stage(long long p, OwnData<NS>& dat) const {
+        const double* Ap = A + (size_t)p * m * d;
+        const double* bp = b + (size_t)p * m;
+        uint64_t mask = rows ? (rows[p] & low_bits(m)) : low_bits(m_rows ? min(max(m_rows[p], 0), m) : m);
+        int cnt = 0;
+        for (int i = 0; i < m; ++i) {
+            if (!((mask >> i) & 1ull)) continue;
+            double g[NS], h;
+            cheby_row<NS>(Ap + (size_t)i * d, __ldg(bp + i), d, false, g, h);
+            dat.put_row(cnt, g);
+            dat.hv[cnt * 32] = h;
+            ++cnt;
+        }
+        dat.m = cnt;
+        dat.cj = d;
+        dat.cs = -1.0;
+    }
+    template <int NS>
+    __device__ void store(long long p, const lane::Result<NS>& res) const {
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        const bool ok = res.status == lane::OPTIMAL;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if (j < d) xc[(size_t)p * d + j] = ok ? res.x[j] : nan;
+            if (j == d) r[p] = ok ? res.x[j] : nan;
+        }
+        status[p] = (int8_t)res.status;
+        if (lp_iters) lp_iters[p] = res.iters;
+    }
+};
+
+#ifndef PB200_OWN_MINB4
+#define PB200_OWN_MINB4 16      // NS = 4: 10 matrix entries, <= 128 registers -> 16 warps per SM
+#endif
+template <int NS, class Prob>
+__global__ void __launch_bounds__(32, NS <= 4 ? PB200_OWN_MINB4 : 8) lane_own_kernel(const Prob prob, long long T, int mr, unsigned long long* counter) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x;
+    OwnData<NS> dat;
+    dat.G = smem + 2 * lane;
+    dat.hv = smem + (size_t)mr * NS * 32 + lane;
+    dat.sz = dat.hv - lane + (size_t)mr * 32 + lane;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32ull);
+        base = __shfl_sync(FULL_MASK, base, 0);
+        if ((long long)base >= T) break;
+        const long long t = (long long)base + lane;
+        const bool has = t < T;
+        dat.m = 0;
+        dat.cj = 0;
+        dat.cs = 0.0;
+        if (has) prob.template stage<NS>(t, dat);
+        __syncwarp();
+        lane::Result<NS> res;
+        lane::lane_solve<NS, OwnData<NS>, lane::WarpLanes>(dat, has, prob.n(), res);
+        if (has) prob.template store<NS>(t, res);
         __syncwarp();
     }
 }

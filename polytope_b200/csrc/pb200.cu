@@ -452,6 +452,41 @@ static int launch_lanes(const Prob& prob, long long P, int m, cudaStream_t st) {
     return PB200_OK;
 }
 
+// independent LPs, one per lane with its own rows (lane_own_kernel): worth it while at least four
+// warps fit on an SM
+template <int NS>
+static bool own_fits(int mr) { return own_smem_doubles<NS>(mr) * sizeof(double) <= 56 * 1024; }
+static bool own_applies(int mr, int n) {
+    if (!g_lane_enabled || n < 1 || n > 8 || mr < 1) return false;
+    return n <= 4 ? own_fits<4>(mr) : own_fits<8>(mr);
+}
+
+template <int NS, class Prob>
+static int launch_own_ns(const Prob& prob, long long T, int mr, cudaStream_t st) {
+    if (!g_lane_counters_ptr) PB_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_lane_counters_ptr, g_lane_counters));
+    unsigned long long* counter = g_lane_counters_ptr + (__atomic_fetch_add(&g_lane_ring, 1u, __ATOMIC_RELAXED) % LANE_COUNTERS);
+    PB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    const size_t smem = own_smem_doubles<NS>(mr) * sizeof(double);
+    auto kern = lane_own_kernel<NS, Prob>;
+    PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!sm_count()) return PB200_ECUDA;
+    int per_sm = 0;
+    PB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    if (per_sm < 1) return fail(PB200_EUNSUPPORTED, "lane LP kernel does not fit on an SM");
+    long long grid = (long long)g_sm_count * per_sm;
+    const long long need = (T + 31) / 32;
+    if (need < grid) grid = need;
+    kern<<<(unsigned)grid, 32, smem, st>>>(prob, T, mr, counter);
+    ++g_launches;
+    PB_CHECK_CUDA(cudaGetLastError());
+    return PB200_OK;
+}
+template <class Prob>
+static int launch_own(const Prob& prob, long long T, int mr, int n, cudaStream_t st) {
+    if (T <= 0) return PB200_OK;
+    return n <= 4 ? launch_own_ns<4>(prob, T, mr, st) : launch_own_ns<8>(prob, T, mr, st);
+}
+
 // ------------------------------------------------------------------------
 // small non-LP kernels of the pipelines (one warp per polytope)
 // ------------------------------------------------------------------------
@@ -778,6 +813,10 @@ int pb200_cheby_batch(const double* A, const double* b, const int32_t* m_rows, c
     if (P == 0) return PB200_OK;
     if (P < 0 || !A || !b || !r || !xc || !status) return fail(PB200_EINVAL, "pb200_cheby_batch: null pointer");
     if (rows && m > 64) return fail(PB200_EUNSUPPORTED, "row masks need m <= 64");
+    if (m <= 64 && own_applies(m, d + 1)) {
+        ChebyOwn prob{A, b, m_rows, rows, m, d, r, xc, status, nullptr};
+        return launch_own(prob, P, m, d + 1, (cudaStream_t)stream);
+    }
     ChebyLP prob{A, b, m_rows, rows, nullptr, 0, m, d, r, xc, status, nullptr};
     return launch_lp(prob, P, m, d + 1, (cudaStream_t)stream);
 }
@@ -833,8 +872,13 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     if (rc) return rc;
     stage_mark(1, st);
     // 2. is_fulldim: one Chebyshev LP per polytope
-    ChebyLP cheb{An, ws.bn, nullptr, ws.valid, nullptr, 0, m, d, r, xc, ws.cheb_status, lp_iters};
-    if ((rc = launch_lp(cheb, P, m, d + 1, st))) return rc;
+    if (own_applies(m, d + 1)) {
+        ChebyOwn cheb{An, ws.bn, nullptr, ws.valid, m, d, r, xc, ws.cheb_status, lp_iters};
+        if ((rc = launch_own(cheb, P, m, d + 1, st))) return rc;
+    } else {
+        ChebyLP cheb{An, ws.bn, nullptr, ws.valid, nullptr, 0, m, d, r, xc, ws.cheb_status, lp_iters};
+        if ((rc = launch_lp(cheb, P, m, d + 1, st))) return rc;
+    }
     stage_mark(2, st);
     // 3. b == inf drop + duplicate-direction filter, then plan
     {
@@ -910,8 +954,27 @@ int pb200_adjacent_pairs(const double* A, const double* b, int ncell, int mc, in
     if (!pair_i && T != (long long)ncell * (ncell - 1) / 2)
         return fail(PB200_EINVAL, "implicit pair enumeration needs T == ncell*(ncell-1)/2");
     if (2 * mc > 64) return fail(PB200_EUNSUPPORTED, "adjacent: need 2*mc <= 64 rows");
+    if (own_applies(2 * mc, d + 1)) {
+        AdjacentOwn prob{A, b, ncell, mc, d, pair_i, pair_j, 0, 0, abs_tol, adjacent, radius, status};
+        return launch_own(prob, T, 2 * mc, d + 1, (cudaStream_t)stream);
+    }
     AdjacentLP prob{A, b, ncell, mc, d, pair_i, pair_j, abs_tol, adjacent, radius, status};
     return launch_lp(prob, T, 2 * mc, d + 1, (cudaStream_t)stream);
+}
+
+int pb200_adjacent_range(const double* A, const double* b, int ncell, int mc, int d, int order, long long t_begin,
+                         long long T, double abs_tol, uint8_t* adjacent, double* radius, int8_t* status, void* stream) {
+    if (T == 0) return PB200_OK;
+    if (!A || !b || !adjacent || T < 0 || t_begin < 0 || ncell < 2) return fail(PB200_EINVAL, "pb200_adjacent_range: bad argument");
+    if (order != 0 && order != 1) return fail(PB200_EINVAL, "pb200_adjacent_range: order must be 0 (j < i) or 1 (all i != j)");
+    const long long total = order == 0 ? (long long)ncell * (ncell - 1) / 2 : (long long)ncell * (ncell - 1);
+    if (t_begin + T > total) return fail(PB200_EINVAL, "pb200_adjacent_range: pair range exceeds the enumeration");
+    if (2 * mc > 64) return fail(PB200_EUNSUPPORTED, "adjacent: need 2*mc <= 64 rows");
+    if (!own_applies(2 * mc, d + 1))
+        return fail(PB200_EUNSUPPORTED, "pb200_adjacent_range: cells too large for the lane kernel; pass explicit pair lists "
+                                        "to pb200_adjacent_pairs");
+    AdjacentOwn prob{A, b, ncell, mc, d, nullptr, nullptr, order, t_begin, abs_tol, adjacent, radius, status};
+    return launch_own(prob, T, 2 * mc, d + 1, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@ from polytope_b200 import _capi
 logger = logging.getLogger(__name__)
 
 F_EMPTY, F_MINREP, F_BBOX, F_LPFAIL = 1, 2, 4, 8
+PB200_EUNSUPPORTED = -2         # include/polytope_b200.h
 ABS_TOL = 1e-7          # polytope/polytope.py:83
 
 
@@ -312,6 +313,32 @@ def adjacent_pairs(A, b, pair_i=None, pair_j=None, abs_tol=ABS_TOL):
     return _out(host, adj, rad, status)
 
 
+def adjacent_range(A, b, order, t_begin, count, abs_tol=ABS_TOL):
+    """is_adjacent over pairs [t_begin, t_begin + count) of an implicit enumeration of the cells'
+    pairs -- the block a rank of a sharded partition job owns, no pair lists in memory.
+    order 0: t = i (i - 1) / 2 + j, j < i (find_adjacent_regions, prop2partition.py:57-61);
+    order 1: all ordered pairs i != j, row-major (compute_adj, prop2partition.py:253-261).
+    -> (adjacent uint8[count], radius[count], status int8[count])"""
+    _require_cuda()
+    lib = _capi.lib()
+    A, host = _dev(A)
+    b, _ = _dev(b)
+    ncell, mc, d = A.shape
+    adj = torch.empty(count, dtype=torch.uint8, device='cuda')
+    rad = torch.empty(count, dtype=torch.float64, device='cuda')
+    status = torch.empty(count, dtype=torch.int8, device='cuda')
+    rc = lib.pb200_adjacent_range(A.data_ptr(), b.data_ptr(), ncell, mc, d, int(order), int(t_begin), int(count),
+                                  float(abs_tol), adj.data_ptr(), rad.data_ptr(), status.data_ptr(), _stream())
+    if rc == PB200_EUNSUPPORTED:
+        # cells too large for the one-LP-per-lane kernel: explicit pair lists, warp-per-LP kernel
+        from polytope_b200 import sharding
+        block = sharding.pair_block if order == 0 else sharding.ordered_pair_block
+        pi, pj = block(ncell, t_begin, t_begin + count, device='cuda')
+        return adjacent_pairs(A if not host else A.cpu(), b if not host else b.cpu(), pi, pj, abs_tol=abs_tol)
+    _capi.check(rc, 'pb200_adjacent_range')
+    return _out(host, adj, rad, status)
+
+
 # ---------------------------------------------------------------------------
 # point-set kernels
 # ---------------------------------------------------------------------------
@@ -514,6 +541,34 @@ def dual_facets_to_vertices(hull, xc):
     return V.cpu().numpy() if host else V
 
 
+def extreme_pipeline(A, b, facet_cap=None, out_cap=None):
+    """extreme() of P stacked full-dimensional polytopes of dimension d >= 3, device tensors in and
+    out (polytope.py:1597-1682): reduce -> Chebyshev centre of the reduced rows -> polar dual ->
+    dual hull -> V = H / K + xc.  No host bookkeeping per polytope (polytope.extreme_batch is the
+    object-level form with the reference's caching and empty / low-dimensional branches).
+    -> (counts int32[P], V[sum(counts), d] in polytope order, hull HullResult, reduce ReduceResult)"""
+    _require_cuda()
+    A, _ = _dev(A)
+    b, _ = _dev(b)
+    P, m, d = A.shape
+    res = reduce_batch(A, b)
+    W = res.keep.shape[1] if res.keep.dim() == 2 else 1
+    shifts = torch.arange(m, device='cuda')
+    if W == 1:
+        bits = ((res.keep.unsqueeze(1) >> shifts) & 1).bool()
+    else:
+        bits = ((res.keep[:, shifts // 64] >> (shifts % 64)) & 1).bool()
+    rows = bits.sum(1).to(torch.int32)
+    order = torch.argsort((~bits).to(torch.int8), dim=1, stable=True)       # kept rows first, original order
+    Ar = torch.gather(res.A, 1, order.unsqueeze(-1).expand(-1, -1, d)).contiguous()
+    br = torch.gather(res.b, 1, order).contiguous()
+    r, xc, st = cheby_batch(Ar, br, rows)
+    dual = dual_points(Ar, br, xc, rows)
+    hull = hull_batch(dual, rows, facet_cap=facet_cap, out_cap=out_cap)
+    V = dual_facets_to_vertices(hull, xc)
+    return hull.facet_cnt, V, hull, res
+
+
 # ---------------------------------------------------------------------------
 # set difference
 # ---------------------------------------------------------------------------
@@ -612,6 +667,18 @@ def profile_read():
 
 def launch_count():
     return int(_capi.lib().pb200_launch_count())
+
+
+def measure_dfma_tflops():
+    """fp64 FMA peak of the current device, measured now (TFLOP/s)."""
+    import ctypes
+    _require_cuda()
+    n = 1024 * torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    scratch = torch.empty(n, dtype=torch.float64, device='cuda')
+    out = ctypes.c_double(0.0)
+    _capi.check(_capi.lib().pb200_measure_dfma_tflops(scratch.data_ptr(), n, ctypes.cast(ctypes.byref(out), ctypes.c_void_p),
+                                                      _stream()), 'pb200_measure_dfma_tflops')
+    return float(out.value)
 
 
 def lane_solver(on=True):

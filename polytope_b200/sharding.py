@@ -80,10 +80,57 @@ def adjacency_sharded(A, b, group=None, abs_tol=1e-7):
     bd = torch.as_tensor(b).to('cuda')
 
     def local(lo, hi):
-        pi, pj = pair_block(ncell, lo, hi, device='cuda')
-        adj, _, _ = engine.adjacent_pairs(Ad, bd, pi, pj, abs_tol=abs_tol)
+        adj, _, _ = engine.adjacent_range(Ad, bd, 0, lo, hi - lo, abs_tol=abs_tol)
         return (adj,)
     return sharded_map(local, T, group)[0]
+
+
+def ordered_pair_block(n_cells, lo, hi, device='cpu'):
+    """Pairs lo..hi-1 of MetricPartition.compute_adj's double loop (prop2partition.py:253-261):
+    all ordered pairs (i, j), i != j, row-major: t = i (n - 1) + jj, j = jj + (jj >= i)."""
+    t = torch.arange(lo, hi, dtype=torch.int64, device=device)
+    i = t // (n_cells - 1)
+    jj = t - i * (n_cells - 1)
+    j = jj + (jj >= i).to(torch.int64)
+    return i.to(torch.int32), j.to(torch.int32)
+
+
+def adjacency_ordered_sharded(A, b, group=None, abs_tol=1e-7):
+    """cfg5 with compute_adj semantics: is_adjacent over all n (n - 1) ordered pairs, the pair
+    range split across the ranks; one all-gather of the uint8 flags.
+    -> flags uint8[n (n - 1)] on every rank (row-major over i, diagonal left out)."""
+    from polytope_b200 import engine
+    ncell = A.shape[0]
+    T = ncell * (ncell - 1)
+    Ad = torch.as_tensor(A).to('cuda')
+    bd = torch.as_tensor(b).to('cuda')
+
+    def local(lo, hi):
+        adj, _, _ = engine.adjacent_range(Ad, bd, 1, lo, hi - lo, abs_tol=abs_tol)
+        return (adj,)
+    return sharded_map(local, T, group)[0]
+
+
+def extreme_tensor_sharded(A, b, group=None, gather_vertices=True, caps=None):
+    """cfg4 on stacked tensors: extreme() of P polytopes (engine.extreme_pipeline), the batch split
+    across the ranks in contiguous blocks; the per-polytope vertex counts are all-gathered and
+    (optionally) the vertices with one padded all-gather.  `caps` = (facet_cap,
+    out_cap) of a previous call avoids the capacity retries.
+    -> (counts int32[P], V, (facet_cap, out_cap))"""
+    from polytope_b200 import engine
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    P = A.shape[0]
+    lo, hi = shard_bounds(P, rank, world)
+    cnt, V, hull, _ = engine.extreme_pipeline(A[lo:hi], b[lo:hi], *(caps or (None, None)))
+    caps = (hull.facet_cap, int(cnt.sum().item()) + 1024)
+    if world == 1:
+        return cnt, V, caps
+    counts = allgather_blocks(cnt, P, group)
+    if not gather_vertices:
+        return counts, V, caps
+    allV, _ = allgather_ragged(V, group)
+    return counts, allV, caps
 
 
 def allgather_ragged(rows, group=None):

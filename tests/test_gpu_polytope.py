@@ -403,3 +403,30 @@ def test_reduce_at_the_largest_advertised_shape():
         assert res.keep_lists()[i] == o['keep']
         assert int(res.n_lp[i]) == o['n_lp']
         assert abs(res.r[i] - o['r']) <= 1e-9
+
+
+def test_adjacent_range_enumerations_equal_pair_lists():
+    """pb200_adjacent_range: both implicit enumerations (find_adjacent_regions' j < i order and
+    compute_adj's ordered pairs, prop2partition.py:57-61, :253-261), whole and in blocks, against
+    explicit pair lists through pb200_adjacent_pairs on both LP kernels, and against geometry."""
+    from polytope_b200 import engine, sharding
+    for shape in ((5, 4), (3, 3, 2), (2, 2, 2, 2)):
+        A, b, idx = wl.box_grid(shape)
+        n = len(A)
+        for order, block in ((0, sharding.pair_block), (1, sharding.ordered_pair_block)):
+            T = n * (n - 1) // (2 if order == 0 else 1)
+            pi, pj = block(n, 0, T)
+            touch = np.abs(idx[pi.numpy()] - idx[pj.numpy()]).max(1) <= 1
+            whole, rad, st = engine.adjacent_range(A, b, order, 0, T)
+            assert np.array_equal(whole.astype(bool), touch) and np.all(st == 0)
+            cut = T // 3
+            parts = np.concatenate([engine.adjacent_range(A, b, order, 0, cut)[0], engine.adjacent_range(A, b, order, cut, T - cut)[0]])
+            assert np.array_equal(parts, whole)
+            lst, rad2, _ = engine.adjacent_pairs(A, b, pi.numpy(), pj.numpy())
+            assert np.array_equal(lst, whole) and np.allclose(rad2, rad, atol=1e-12, equal_nan=True)
+            engine.lane_solver(False)
+            try:
+                warp, rad3, _ = engine.adjacent_pairs(A, b, pi.numpy(), pj.numpy())
+            finally:
+                engine.lane_solver(True)
+            assert np.array_equal(warp, whole) and np.allclose(rad3, rad, atol=1e-11, equal_nan=True)

@@ -37,6 +37,21 @@ def test_pair_block_enumeration_matches_tril_order():
             assert np.array_equal(np.concatenate(got_i), ii) and np.array_equal(np.concatenate(got_j), jj)
 
 
+def test_ordered_pair_block_matches_compute_adj_order():
+    """cfg5 with compute_adj semantics (prop2partition.py:253-261): all ordered pairs i != j in
+    the order of the reference's double loop, whatever the split across ranks."""
+    for n in (2, 3, 10, 1024):
+        ii, jj = np.nonzero(~np.eye(n, dtype=bool))
+        for world in (1, 2, 8):
+            got_i, got_j = [], []
+            for r in range(world):
+                lo, hi = sharding.shard_bounds(n * (n - 1), r, world)
+                i, j = sharding.ordered_pair_block(n, lo, hi)
+                got_i.append(i.numpy())
+                got_j.append(j.numpy())
+            assert np.array_equal(np.concatenate(got_i), ii) and np.array_equal(np.concatenate(got_j), jj)
+
+
 def _worker(rank, world, port, n_items, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)

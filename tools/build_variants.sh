@@ -9,11 +9,11 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 while [ $# -ge 2 ]; do
     name=$1; flags=$2; shift 2
     tmp=$(mktemp -d)
-    for f in pb200 sets hull diff; do
+    for f in pb200 sets hull diff peak; do
         nvcc -O3 -lineinfo -std=c++17 $ARCH -Xcompiler -fPIC $flags -c -o $tmp/$f.o $f.cu &
     done
     wait
-    nvcc $ARCH -shared -o ../ab/$name.so $tmp/pb200.o $tmp/sets.o $tmp/hull.o $tmp/diff.o
+    nvcc $ARCH -shared -o ../ab/$name.so $tmp/pb200.o $tmp/sets.o $tmp/hull.o $tmp/diff.o $tmp/peak.o
     rm -rf $tmp
     echo "built ab/$name.so  ($flags)"
 done
