@@ -131,4 +131,9 @@ def test_extreme_sharded_single_rank_equals_batch():
     counts, V = sharding.extreme_sharded(polys)
     ref = pc.extreme_batch([pc.Polytope(p.A, p.b) for p in polys])
     assert counts.tolist() == [len(v) for v in ref]
-    np.testing.assert_allclose(V.cpu().numpy(), np.concatenate(ref, 0), atol=1e-12)   # ref re-normalises the rows
+    # the hull kernel emits facets in the order its warps finish: vertex order differs between runs
+    Vh = V.cpu().numpy()
+    off = 0
+    for v in ref:
+        assert rows_as_set_close(Vh[off:off + len(v)], v, 1e-12)      # ref re-normalises the rows
+        off += len(v)

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read on the CPU box): key raw metrics, stall mix and
-the hottest source lines.  Usage: tools/ncu_summary.py rep.ncu-rep [n_units] > profiles/x.txt"""
+the hottest source lines.  Usage: tools/ncu_summary.py rep.ncu-rep [n_units] [kernel-name substring] > profiles/x.txt
+(with a substring the raw metrics are those of the first launch whose name contains it; the source page is
+then restricted to that launch)"""
 import collections
 import csv
 import io
@@ -8,7 +10,8 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-units = float(sys.argv[2]) if len(sys.argv) > 2 else None
+units = float(sys.argv[2]) if len(sys.argv) > 2 and float(sys.argv[2]) > 0 else None
+pattern = sys.argv[3] if len(sys.argv) > 3 else None
 
 
 def ncu(*args):
@@ -16,7 +19,11 @@ def ncu(*args):
 
 
 rows = list(csv.reader(io.StringIO(ncu('--page', 'raw', '--csv'))))
-hdr, unit, vals = rows[0], rows[1], rows[2]
+hdr, unit = rows[0], rows[1]
+vals, launch = rows[2], 0
+if pattern:
+    launch = [k for k, r in enumerate(rows[2:]) if pattern in dict(zip(hdr, r)).get('Kernel Name', '')][0]
+    vals = rows[2 + launch]
 raw = dict(zip(hdr, zip(unit, vals)))
 print('# ncu summary of', rep)
 print('kernel:', raw.get('Kernel Name', ('', '?'))[1], ' grid', raw.get('Grid Size', ('', '?'))[1],
@@ -44,7 +51,8 @@ for k in sorted(raw):
         if v >= 0.02:
             print('  %-28s %.3f' % (k[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')], v))
 
-src = list(csv.reader(io.StringIO(ncu('--page', 'source', '--print-source', 'cuda,sass', '--csv'))))
+sel = ['--launch-skip', str(launch), '--launch-count', '1']
+src = list(csv.reader(io.StringIO(ncu('--page', 'source', '--print-source', 'cuda,sass', '--csv', *sel))))
 hdr = None
 cur = None
 lines = []
