@@ -10,20 +10,27 @@
 #include "common.cuh"
 #include "staging.cuh"
 #include "normalize.cuh"      // bulk-copy / mbarrier wrappers
-#include "lp_lane.cuh"
+#include "lp_lane_wide.cuh"
 
 namespace pb200 {
 
-constexpr int LANE_NS = 8;       // padded columns of the lane solver
-constexpr int LANE_NG = 3;       // polytopes a warp holds per round
+// The kernels are instantiated for NS = 8 padded columns (lane_solve, everything in registers)
+// and NS = 12 / 16 (lane_solve_wide, the factor in a lane-interleaved shared-memory array).
+constexpr int LANE_NS = 8;
+template <int NS> PBL_CX int lane_ng() { return NS <= 8 ? 3 : 2; }     // polytopes a warp holds per round
+template <int NS> PBL_CX int lane_nt() { return NS * (NS + 1) / 2; }
 #ifndef PB200_LANE_MINB
 #define PB200_LANE_MINB 8
 #endif
 
-__host__ __device__ inline int lane_slot_doubles(int m) { return m * LANE_NS + 4; }   // +4: slots land in different banks
+template <int NS>
+__host__ __device__ inline int lane_slot_doubles(int m) { return m * NS + 4; }   // +4: slots land in different banks
 // G[NG][slot] | hA[NG][m] | hB[NG][m] | sz[2 m][32] | raw[m NS + m] (landing zone of the bulk copies) | mbarrier
+// | (NS > 8) L[NT][32]
+template <int NS>
 __host__ __device__ inline size_t lane_smem_doubles(int m) {
-    return (size_t)LANE_NG * lane_slot_doubles(m) + 2 * LANE_NG * m + 64 * (size_t)m + (size_t)m * LANE_NS + m + 2;
+    return (size_t)lane_ng<NS>() * lane_slot_doubles<NS>(m) + 2 * lane_ng<NS>() * m + 64 * (size_t)m + (size_t)m * NS + m + 2 +
+           (NS > 8 ? (size_t)lane_nt<NS>() * 32 : 0);
 }
 
 // per-warp staging context: where the TMA engine lands a polytope's (A, b) block
@@ -34,35 +41,39 @@ struct LaneStage {
 };
 
 // what a lane sees of its LP
+template <int NS>
 struct LaneData {
-    const double* G;     // [rows][LANE_NS] row-major, shared by the lanes of the same polytope
+    const double* G;     // [rows][NS] row-major, shared by the lanes of the same polytope
     const double* hA;    // right-hand side
     const double* hB;    // right-hand side after the reference's +0.1 / -0.1 round trip (rows before k)
     double* sz;          // this lane's (s_i, z_i): sz[(2 i) * 32], sz[(2 i + 1) * 32]
+    double* Lm;          // NS > 8: this lane's packed factor, entry e at Lm[e * 32]
     int m, k;            // rows; row whose h carries +0.1 (-1: none)
     int cj;              // objective: cs * e_cj, or -G[k] when cj < 0
     double cs;
     __device__ __forceinline__ int rows() const { return m; }
-    __device__ __forceinline__ void row(int i, double (&g)[LANE_NS]) const {
-        const double2* p = reinterpret_cast<const double2*>(G + i * LANE_NS);
+    __device__ __forceinline__ void row(int i, double (&g)[NS]) const {
+        const double2* p = reinterpret_cast<const double2*>(G + i * NS);
 #pragma unroll
-        for (int j = 0; j < LANE_NS / 2; ++j) { const double2 v = p[j]; g[2 * j] = v.x; g[2 * j + 1] = v.y; }
+        for (int j = 0; j < NS / 2; ++j) { const double2 v = p[j]; g[2 * j] = v.x; g[2 * j + 1] = v.y; }
     }
     __device__ __forceinline__ double h(int i) const {
         const double* src = i < k ? hB : hA;          // rows before k carry the +0.1 / -0.1 round trip
         const double a = src[i];
         return i == k ? __dadd_rn(a, 0.1) : a;
     }
-    __device__ __forceinline__ double c(int j) const { return cj < 0 ? -G[k * LANE_NS + j] : (j == cj ? cs : 0.0); }
+    __device__ __forceinline__ double c(int j) const { return cj < 0 ? -G[k * NS + j] : (j == cj ? cs : 0.0); }
     __device__ __forceinline__ double& s(int i) { return sz[(2 * i) * 32]; }
     __device__ __forceinline__ double& z(int i) { return sz[(2 * i + 1) * 32]; }
+    __device__ __forceinline__ double& L(int e) { return Lm[e * 32]; }
 };
 
-// rows selected by `mask` (ascending) of a row-major [m x d] matrix -> row-major [cnt][LANE_NS], zero padded.
+// rows selected by `mask` (ascending) of a row-major [m x d] matrix -> row-major [cnt][NS], zero padded.
 // The polytope's (A, b) block is one contiguous span each: when the spans are 16-byte aligned they
 // are fetched by two 1-D bulk async copies (cp.async.bulk, the TMA engine; SASS UBLKCP) that
 // complete on the warp's mbarrier, and the rows are picked / padded out of shared memory;
 // otherwise by coalesced loads.
+template <int NS>
 __device__ __forceinline__ int lane_stage_masked(const double* __restrict__ Ap, const double* __restrict__ bp, int m, int d,
                                                  uint64_t mask, double* G, double* hA, int lane, LaneStage& sg) {
     const int cnt = __popcll(mask);
@@ -76,21 +87,21 @@ __device__ __forceinline__ int lane_stage_masked(const double* __restrict__ Ap, 
             bulk_load(sg.raw + total, bp, (uint32_t)(m * sizeof(double)), sg.bar);
         }
     }
-    for (int e = lane; e < cnt * LANE_NS; e += 32) G[e] = 0.0;
+    for (int e = lane; e < cnt * NS; e += 32) G[e] = 0.0;
     __syncwarp();
     if (bulk) {
         mbar_wait(sg.bar, sg.parity);
         sg.parity ^= 1u;
         for (int e = lane; e < total; e += 32) {
             const int i = e / d, j = e - i * d;
-            if ((mask >> i) & 1ull) G[__popcll(mask & ((1ull << i) - 1ull)) * LANE_NS + j] = sg.raw[e];
+            if ((mask >> i) & 1ull) G[__popcll(mask & ((1ull << i) - 1ull)) * NS + j] = sg.raw[e];
         }
         for (int i = lane; i < m; i += 32)
             if ((mask >> i) & 1ull) hA[__popcll(mask & ((1ull << i) - 1ull))] = sg.raw[total + i];
     } else {
         for (int e = lane; e < total; e += 32) {
             const int i = e / d, j = e - i * d;
-            if ((mask >> i) & 1ull) G[__popcll(mask & ((1ull << i) - 1ull)) * LANE_NS + j] = __ldg(Ap + e);
+            if ((mask >> i) & 1ull) G[__popcll(mask & ((1ull << i) - 1ull)) * NS + j] = __ldg(Ap + e);
         }
         for (int i = lane; i < m; i += 32)
             if ((mask >> i) & 1ull) hA[__popcll(mask & ((1ull << i) - 1ull))] = __ldg(bp + i);
@@ -100,9 +111,10 @@ __device__ __forceinline__ int lane_stage_masked(const double* __restrict__ Ap, 
 }
 
 // Polytope.__init__ normalisation of the staged rows (polytope.py:128-138), numpy's summation order
+template <int NS>
 __device__ __forceinline__ void lane_renormalize(double* G, double* hA, int cnt, int d, int lane) {
     for (int i = lane; i < cnt; i += 32) {
-        double* row = G + i * LANE_NS;
+        double* row = G + i * NS;
         const double nrm = sqrt(np_sum_squares([&](int j) { return row[j]; }, d));
         if (nrm > 1e-10) {
             const double mult = __ddiv_rn(1.0, nrm);
@@ -133,14 +145,17 @@ struct RowLanes {
         if (!(flags[p] & run_mask)) return 0;
         return __popcll(rows[p] & low_bits(m));
     }
+    template <int NS>
     __device__ int stage(long long p, double* G, double* hA, double* hB, int lane, LaneStage& sg) const {
-        const int cnt = lane_stage_masked(A + (size_t)p * m * d, b + (size_t)p * m, m, d, rows[p] & low_bits(m), G, hA, lane, sg);
+        const int cnt = lane_stage_masked<NS>(A + (size_t)p * m * d, b + (size_t)p * m, m, d, rows[p] & low_bits(m), G, hA, lane, sg);
         for (int i = lane; i < cnt; i += 32) hB[i] = __dadd_rn(__dadd_rn(hA[i], 0.1), -0.1);
         __syncwarp();
         return cnt;
     }
-    __device__ void setup(LaneData& dat, int k) const { dat.k = k; dat.cj = -1; dat.cs = 0.0; }
-    __device__ void store(long long p, int k, const lane::Result<LANE_NS>& res) const {
+    template <int NS>
+    __device__ void setup(LaneData<NS>& dat, int k) const { dat.k = k; dat.cj = -1; dat.cs = 0.0; }
+    template <int NS>
+    __device__ void store(long long p, int k, const lane::Result<NS>& res) const {
         const uint64_t mask = rows[p] & low_bits(m);
         const int orig = nth_set_bit(mask, k);
         bool kept = false;
@@ -173,40 +188,48 @@ struct BboxLanes {
         if (need_flags && !(need_flags[p] & need_mask)) return 0;
         return 2 * d;
     }
+    template <int NS>
     __device__ int stage(long long p, double* G, double* hA, double* hB, int lane, LaneStage& sg) const {
         uint64_t mask;
         if (rows) mask = rows[p] & low_bits(m);
         else mask = low_bits(m_rows ? min(max(m_rows[p], 0), m) : m);
-        const int cnt = lane_stage_masked(A + (size_t)p * m * d, b + (size_t)p * m, m, d, mask, G, hA, lane, sg);
-        if (renorm) lane_renormalize(G, hA, cnt, d, lane);
+        const int cnt = lane_stage_masked<NS>(A + (size_t)p * m * d, b + (size_t)p * m, m, d, mask, G, hA, lane, sg);
+        if (renorm) lane_renormalize<NS>(G, hA, cnt, d, lane);
         return cnt;
     }
-    __device__ void setup(LaneData& dat, int q) const {
+    template <int NS>
+    __device__ void setup(LaneData<NS>& dat, int q) const {
         dat.k = -1;
         dat.cj = q < d ? q : q - d;
         dat.cs = q < d ? 1.0 : -1.0;
     }
-    __device__ void store(long long p, int q, const lane::Result<LANE_NS>& res) const {
+    template <int NS>
+    __device__ void store(long long p, int q, const lane::Result<NS>& res) const {
         const int i = q < d ? q : q - d;
-        (q < d ? val_lo : val_hi)[p * d + i] = res.status == lane::OPTIMAL ? res.x[i] : 0.0;
+        double xi = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+            if (j == i) xi = res.x[j];
+        (q < d ? val_lo : val_hi)[p * d + i] = res.status == lane::OPTIMAL ? xi : 0.0;
         status[p * 2 * d + q] = (int8_t)res.status;
         if (need_flags && (res.status == lane::ITER_LIMIT || res.status == lane::NUMERICAL)) atomicOr(need_flags + p, retry_bit);
         if (lp_iters) atomicAdd(lp_iters + p, res.iters);
     }
 };
 
-template <class Prob>
-__global__ void __launch_bounds__(32, PB200_LANE_MINB) lane_kernel(const Prob prob, long long P, int m, unsigned long long* counter) {
+template <int NS, class Prob>
+__global__ void __launch_bounds__(32, NS <= 8 ? PB200_LANE_MINB : 2) lane_kernel(const Prob prob, long long P, int m, unsigned long long* counter) {
     extern __shared__ __align__(16) double smem[];
+    constexpr int LANE_NG = lane_ng<NS>();
     const int lane = threadIdx.x;
-    const int GS = lane_slot_doubles(m);
+    const int GS = lane_slot_doubles<NS>(m);
     double* G = smem;
     double* hA = G + LANE_NG * GS;
     double* hB = hA + LANE_NG * m;
     double* sz = hB + LANE_NG * m;
     LaneStage sg;
     sg.raw = sz + 64 * (size_t)m;
-    sg.bar = reinterpret_cast<uint64_t*>(sg.raw + (size_t)m * LANE_NS + m + (m & 1));
+    sg.bar = reinterpret_cast<uint64_t*>(sg.raw + (size_t)m * NS + m + (m & 1));
     sg.parity = 0;
     if (lane == 0) mbar_init(sg.bar, 1);
     __syncwarp();
@@ -232,7 +255,7 @@ __global__ void __launch_bounds__(32, PB200_LANE_MINB) lane_kernel(const Prob pr
             }
             const int cnt = prob.count(p);
             if (cnt - k0 <= 0) continue;
-            const int rows = prob.stage(p, G + ns * GS, hA + ns * m, hB + ns * m, lane, sg);
+            const int rows = prob.template stage<NS>(p, G + ns * GS, hA + ns * m, hB + ns * m, lane, sg);
             const int take = min(cnt - k0, 32 - nl);
             if (lane >= nl && lane < nl + take) { my_p = p; my_k = k0 + lane - nl; my_slot = ns; my_rows = rows; }
             nl += take;
@@ -241,16 +264,18 @@ __global__ void __launch_bounds__(32, PB200_LANE_MINB) lane_kernel(const Prob pr
         }
         if (nl == 0) break;
         __syncwarp();
-        LaneData dat;
+        LaneData<NS> dat;
         dat.G = G + my_slot * GS;
         dat.hA = hA + my_slot * m;
         dat.hB = hB + my_slot * m;
         dat.sz = sz + lane;
+        dat.Lm = reinterpret_cast<double*>(sg.bar + 1) + lane;
         dat.m = my_rows;
-        prob.setup(dat, my_k);
-        lane::Result<LANE_NS> res;
-        lane::lane_solve<LANE_NS, LaneData, lane::WarpLanes>(dat, my_p >= 0, prob.n(), res);
-        if (my_p >= 0) prob.store(my_p, my_k, res);
+        prob.template setup<NS>(dat, my_k);
+        lane::Result<NS> res;
+        if constexpr (NS <= 8) lane::lane_solve<NS, LaneData<NS>, lane::WarpLanes>(dat, my_p >= 0, prob.n(), res);
+        else lane::lane_solve_wide<NS, LaneData<NS>, lane::WarpLanes>(dat, my_p >= 0, prob.n(), res);
+        if (my_p >= 0) prob.template store<NS>(my_p, my_k, res);
         __syncwarp();
     }
 }
@@ -426,6 +451,10 @@ struct ChebyOwn {
         if (lp_iters) lp_iters[p] = res.iters;
     }
 };
+
+// (A one-LP-per-lane kernel for Chebyshev LPs of 9 <= n <= 16 columns that read the rows from global memory was
+// measured in r02h and dropped: 0.72 vs 0.42 ms on cfg2's 10 000 LPs and 1.8 vs 0.1 ms on cfg4's 1000 against the
+// warp-per-LP kernel -- one LP per polytope leaves too few warps, and every row pass waits for L2.)
 
 #ifndef PB200_OWN_MINB4
 #define PB200_OWN_MINB4 16      // NS = 4: 10 matrix entries, <= 128 registers -> 16 warps per SM

@@ -428,17 +428,22 @@ __device__ unsigned long long g_lane_counters[LANE_COUNTERS];
 static unsigned long long* g_lane_counters_ptr = nullptr;
 static unsigned g_lane_ring = 0;
 
-static bool lane_applies(int m, int n) { return g_lane_enabled && n >= 1 && n <= LANE_NS && m >= 1 && m <= 64; }
+// n <= 12: always (r02j, one B200: cfg2 2.0x, d = 10 3.1x, cfg4's n = 12 1.7x over the warp-per-LP kernels);
+// 13 <= n <= 16 (136-entry factor, two warps per SM): break-even at 500 polytopes, so only for batches
+// that fill the GPU several times over
+static bool lane_applies(int m, int n, long long P) {
+    return g_lane_enabled && n >= 1 && m >= 1 && m <= 64 && (n <= 12 || (n <= 16 && P >= 2000));
+}
 
-template <class Prob>
-static int launch_lanes(const Prob& prob, long long P, int m, cudaStream_t st) {
+template <int NS, class Prob>
+static int launch_lanes_ns(const Prob& prob, long long P, int m, cudaStream_t st) {
     if (P <= 0) return PB200_OK;
     if (!g_lane_counters_ptr) PB_CHECK_CUDA(cudaGetSymbolAddress((void**)&g_lane_counters_ptr, g_lane_counters));
     // one work counter per launch in flight (launches of different streams may overlap)
     unsigned long long* counter = g_lane_counters_ptr + (__atomic_fetch_add(&g_lane_ring, 1u, __ATOMIC_RELAXED) % LANE_COUNTERS);
     PB_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-    const size_t smem = lane_smem_doubles(m) * sizeof(double);
-    auto kern = lane_kernel<Prob>;
+    const size_t smem = lane_smem_doubles<NS>(m) * sizeof(double);
+    auto kern = lane_kernel<NS, Prob>;
     PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!sm_count()) return PB200_ECUDA;
     int per_sm = 0;
@@ -450,6 +455,14 @@ static int launch_lanes(const Prob& prob, long long P, int m, cudaStream_t st) {
     ++g_launches;
     PB_CHECK_CUDA(cudaGetLastError());
     return PB200_OK;
+}
+// n <= 8: everything in registers; 9 <= n <= 16: lane_solve_wide (padded to 12 or 16 columns)
+template <class Prob>
+static int launch_lanes(const Prob& prob, long long P, int m, cudaStream_t st) {
+    const int n = prob.d;
+    if (n <= 8) return launch_lanes_ns<8>(prob, P, m, st);
+    if (n <= 12) return launch_lanes_ns<12>(prob, P, m, st);
+    return launch_lanes_ns<16>(prob, P, m, st);
 }
 
 // independent LPs, one per lane with its own rows (lane_own_kernel): worth it while at least four
@@ -830,7 +843,7 @@ int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows, in
     // the LP kernel writes the raw optimised coordinates into lo / hi, the
     // resolve kernel then applies the reference's status conventions in place
     int rc;
-    if (lane_applies(m, d)) {
+    if (lane_applies(m, d, P)) {
         BboxLanes prob{A, b, m_rows, nullptr, nullptr, 0, 0, m, d, 0, lo, hi, status, nullptr};
         rc = launch_lanes(prob, P, m, (cudaStream_t)stream);
     } else {
@@ -896,7 +909,7 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     }
     stage_mark(3, st);
     // 4. bounding box of Polytope(A_arr, b_arr) where neq > 3 nx
-    if (lane_applies(m, d)) {
+    if (lane_applies(m, d, P)) {
         BboxLanes bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, CTL_RETRY_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
         if ((rc = launch_lanes(bb, P, m, st))) return rc;
         // safety net: polytopes with an LP the lane solver could not finish (none on the BASELINE
@@ -916,7 +929,7 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     stage_mark(5, st);
     // 6. one LP per surviving row
     PB_CHECK_CUDA(cudaMemsetAsync(ws.keep_lp, 0, sizeof(uint64_t) * P, st));
-    if (lane_applies(m, d)) {
+    if (lane_applies(m, d, P)) {
         RowLanes row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, CTL_RETRY_ROWS, m, d, abs_tol, ws.keep_lp, lp_iters};
         if ((rc = launch_lanes(row, P, m, st))) return rc;
         RowLP again{An, ws.bn, ws.rows2, flags, CTL_RETRY_ROWS, m, d, abs_tol, ws.keep_lp, lp_iters};

@@ -3,19 +3,24 @@
 // arithmetic against HiGHS without a GPU.  One LP per call, SingleLane policy.
 //   lane_host <in.bin> <out.bin> [w]      (w: WaitingLane policy, every polish preceded by the full wait)
 // in:  int32 B, m, n, then per LP: int32 rows, G[m][n], h[m], c[n] (doubles, row-major)
-// out: per LP: int32 status, iters, polishes, pad; double fun; double x[8]
+// out: per LP: int32 status, iters, polishes, pad; double fun; double x[NS]
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../polytope_b200/csrc/lp_lane.cuh"
+// -DLANE_HOST_NS=12 / 16 builds the wide solver (lp_lane_wide.cuh, 9 <= n <= 16) instead.
+#include "../polytope_b200/csrc/lp_lane_wide.cuh"
 
 using namespace pb200::lane;
-constexpr int NS = 8;
+#ifndef LANE_HOST_NS
+#define LANE_HOST_NS 8
+#endif
+constexpr int NS = LANE_HOST_NS;
 
 struct HostData {
     const double* G; const double* hv; const double* cv;
     int m, n;
-    std::vector<double> sv, zv;
+    std::vector<double> sv, zv, Lv;
+    double& L(int e) { return Lv[e]; }
     int rows() const { return m; }
     void row(int i, double (&g)[NS]) const { for (int j = 0; j < NS; ++j) g[j] = j < n ? G[i * n + j] : 0.0; }
     double h(int i) const { return hv[i]; }
@@ -39,10 +44,17 @@ int main(int argc, char** argv) {
         if (fread(G.data(), sizeof(double), (size_t)m * n, f) != (size_t)m * n) return 5;
         if (fread(h.data(), sizeof(double), m, f) != (size_t)m) return 5;
         if (fread(c.data(), sizeof(double), n, f) != (size_t)n) return 5;
-        HostData d{G.data(), h.data(), c.data(), rows, n, std::vector<double>(m), std::vector<double>(m)};
+        HostData d{G.data(), h.data(), c.data(), rows, n, std::vector<double>(m), std::vector<double>(m),
+                   std::vector<double>(NS * (NS + 1) / 2)};
         Result<NS> res;
-        if (argc > 3 && argv[3][0] == 'w') lane_solve<NS, HostData, WaitingLane>(d, true, n, res);
-        else lane_solve<NS, HostData, SingleLane>(d, true, n, res);
+        const bool waiting = argc > 3 && argv[3][0] == 'w';
+        if (NS > 8) {
+            if (waiting) lane_solve_wide<NS, HostData, WaitingLane>(d, true, n, res);
+            else lane_solve_wide<NS, HostData, SingleLane>(d, true, n, res);
+        } else {
+            if (waiting) lane_solve<NS, HostData, WaitingLane>(d, true, n, res);
+            else lane_solve<NS, HostData, SingleLane>(d, true, n, res);
+        }
         int meta[4] = {res.status, res.iters, res.polishes, 0};
         fwrite(meta, sizeof(int), 4, o);
         fwrite(&res.fun, sizeof(double), 1, o);

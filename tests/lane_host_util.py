@@ -10,21 +10,25 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 NS = 8
 
 
-def build(extra=()):
+def build(extra=(), ns=8):
+    """ns = 8: lane_solve (n <= 8); ns = 12 / 16: lane_solve_wide."""
+    extra = tuple(extra) + (('-DLANE_HOST_NS=%d' % ns,) if ns != 8 else ())
     exe = os.path.join(tempfile.gettempdir(), 'pb200_lane_host_%d' % os.getuid() + ''.join(extra).replace('-', '_').replace('=', '_'))
     src = os.path.join(HERE, 'lane_host.cpp')
-    hdr = os.path.join(os.path.dirname(HERE), 'polytope_b200', 'csrc', 'lp_lane.cuh')
-    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    csrc = os.path.join(os.path.dirname(HERE), 'polytope_b200', 'csrc')
+    hdrs = [os.path.join(csrc, 'lp_lane.cuh'), os.path.join(csrc, 'lp_lane_wide.cuh')]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-o', exe, src] + list(extra))
     return exe
 
 
-def solve(lps, exe=None, waiting=False):
+def solve(lps, exe=None, waiting=False, ns=8):
     """lps: list of (c, G, h).  -> status[B], iters[B], polishes[B], fun[B], X[B, n]"""
-    exe = exe or build()
+    exe = exe or build(ns=ns)
     m = max(len(h) for _, _, h in lps)
     n = len(lps[0][0])
-    assert n <= NS
+    assert n <= ns
+    NS = ns
     with tempfile.TemporaryDirectory() as tmp:
         fin, fout = os.path.join(tmp, 'in.bin'), os.path.join(tmp, 'out.bin')
         with open(fin, 'wb') as f:

@@ -101,3 +101,68 @@ def test_random_lps_every_status_against_highs():
         sel = [k for k, lp in enumerate(lps) if len(lp[0]) == n]
         if sel:
             _check([lps[k] for k in sel], st[sel], np.array(fun)[sel])
+
+
+@pytest.mark.parametrize('ns', [12, 16])
+def test_wide_solver_random_lps_every_status_against_highs(ns):
+    """lane_solve_wide (9 <= n <= 16: the factor in a lane-interleaved array, register-blocked normal matrix)."""
+    rng = np.random.default_rng(5 + ns)
+    lps, st, fun = [], [], []
+    for k in range(160):
+        n = int(rng.integers(9, ns + 1))
+        m = int(rng.integers(1, 60))
+        G = rng.standard_normal((m, n))
+        kind = k % 5
+        if kind == 1:
+            G[:, -1] = G[:, 0]
+        if kind == 2 and m > 1:
+            G[1] = -G[0]
+        h = rng.uniform(0.1, 2.0, m)
+        if kind == 2 and m > 1:
+            h[1] = -h[0] - 1.0
+        if kind == 3:
+            G = np.vstack([np.eye(n), -np.eye(n), G])
+            h = np.hstack([np.ones(2 * n), h])
+        c = rng.standard_normal(n)
+        sol = optimize.linprog(c, G, h, bounds=(None, None))
+        if sol.status not in (0, 2, 3):
+            continue
+        lps.append((c, G, h))
+        st.append(sol.status)
+        fun.append(sol.fun if sol.status == 0 else np.nan)
+    st = np.array(st, dtype=np.int32)
+    fun = np.array(fun)
+    assert {0, 2, 3} <= set(st.tolist())
+    for n in range(9, ns + 1):
+        sel = [k for k, lp in enumerate(lps) if len(lp[0]) == n]
+        if sel:
+            s2, it, pol, f2, X = lh.solve([lps[k] for k in sel], ns=ns)
+            assert np.array_equal(s2, st[sel])
+            ok = st[sel] == 0
+            assert np.all(np.abs(f2[ok] - fun[sel][ok]) <= 1e-7 * (1 + np.abs(fun[sel][ok])))
+
+
+def test_wide_solver_on_the_lps_of_cfg4_reduce():
+    """Every n = 12 LP (bounding box + rows) and the n = 13 Chebyshev LP that reduce() solves on cfg4 polytopes."""
+    rec = []
+    orig = orc.lpsolve
+
+    def recording(c, G, h):
+        sol = orig(c, G, h)
+        rec.append((np.array(c, float), np.array(G, float), np.array(h, float), sol['status'], sol['fun']))
+        return sol
+    orc.lpsolve = recording
+    try:
+        for i in range(2):
+            orc.reduce(*wl.box_cuts(4000 + i, 64, 12))
+    finally:
+        orc.lpsolve = orig
+    for n, ns in ((12, 12), (12, 16), (13, 16)):
+        sel = [r for r in rec if r[1].shape[1] == n]
+        s2, it, pol, f2, X = lh.solve([r[:3] for r in sel], ns=ns)
+        st = np.array([r[3] for r in sel])
+        fun = np.array([np.nan if r[4] is None else r[4] for r in sel])
+        assert np.array_equal(s2, st)
+        ok = st == 0
+        assert np.abs(f2[ok] - fun[ok]).max() <= 1e-9
+        assert it.mean() < 6

@@ -125,7 +125,7 @@ def test_reduce_batch_matches_reference_golden(golden, tag):
 @pytest.mark.parametrize('cfg,n,m,d,ss', [(2, 256, 32, 8, False), (3, 256, 16, 6, True),
                                            (4, 32, 64, 12, False), (6, 24, 64, 16, False),
                                            (12, 128, 24, 4, True), (13, 128, 12, 2, True),
-                                           (14, 64, 40, 3, False)])
+                                           (14, 64, 40, 3, False), (15, 48, 40, 10, False), (16, 24, 56, 14, True)])
 def test_reduce_batch_vs_oracle(cfg, n, m, d, ss):
     """Fresh seeds (not in the golden files): kept rows, flags, LP counts and the
     drifted b identical to the oracle; the normalised A bit-identical to numpy's."""
@@ -363,8 +363,18 @@ def test_host_batches_are_pipelined_and_equal_the_device_path():
     rows = np.random.default_rng(0).integers(2 * d, m + 1, P).astype(np.int32)
     dev = engine.reduce_batch(torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(rows).cuda())
     host = engine.reduce_batch(A, b, rows)
-    for name in ('keep', 'flags', 'n_lp', 'r', 'xc', 'b', 'A'):
+    for name in ('keep', 'flags', 'n_lp', 'b', 'A'):
         assert np.array_equal(np.asarray(getattr(host, name)), getattr(dev, name).cpu().numpy(), equal_nan=True), name
+    # the lane kernels solve 32 LPs per warp in lockstep and a lane's polish step waits for its warp mates, so
+    # the last bits of an LP's solution depend on which LPs share its warp -- chunking regroups them
+    r = dev.r.cpu().numpy()
+    np.testing.assert_allclose(np.asarray(host.r), r, rtol=0, atol=1e-12, equal_nan=True)
+    # the Chebyshev centre is not unique (polytope.py:1245-1246): each path's centre must admit the ball
+    An, bn = np.asarray(host.A), np.asarray(host.b)
+    live = np.arange(m)[None, :] < rows[:, None]
+    for xc in (np.asarray(host.xc), dev.xc.cpu().numpy()):
+        slack = bn - np.einsum('pij,pj->pi', An, xc) - r[:, None]
+        assert slack[live & np.isfinite(slack)].min() >= -1e-9
     slim = engine.reduce_batch(torch.from_numpy(A).pin_memory(), torch.from_numpy(b).pin_memory(), rows,
                                want_A=False, want_b=False)
     assert slim.A is None and slim.b is None and np.array_equal(slim.keep, host.keep)
@@ -430,3 +440,30 @@ def test_adjacent_range_enumerations_equal_pair_lists():
             finally:
                 engine.lane_solver(True)
             assert np.array_equal(warp, whole) and np.allclose(rad3, rad, atol=1e-11, equal_nan=True)
+
+
+@pytest.mark.parametrize('cfg,n,m,d,sample', [(4, 2048, 64, 16, 12), (4, 600, 48, 11, 16), (4, 2048, 50, 13, 12)])
+def test_wide_lane_solver_equals_the_warp_solver_and_the_oracle(cfg, n, m, d, sample):
+    """9 <= n <= 16 columns: one LP per lane with the factor in shared memory (lp_lane_wide.cuh; n >= 13 only for
+    batches of >= 2000 polytopes).  Every keep mask / flag / LP count equals the warp-per-LP path's, a sample the oracle's."""
+    import torch
+    from polytope_b200 import engine
+    from oracle import polytope_oracle as orc
+    A, b = wl.box_cuts_batch(cfg, n, m, d, first=900)
+    Ad, bd = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
+    launches = engine.launch_count()
+    lane = engine.reduce_batch(Ad, bd, want_A=False)
+    n_launch = engine.launch_count() - launches
+    try:
+        engine.lane_solver(False)
+        warp = engine.reduce_batch(Ad, bd, want_A=False)
+    finally:
+        engine.lane_solver(True)
+    assert n_launch == 10          # 8 kernels of the pipeline + the two (empty) retry launches of the lane path
+    assert torch.equal(lane.keep, warp.keep) and torch.equal(lane.flags, warp.flags) and torch.equal(lane.n_lp, warp.n_lp)
+    assert not bool((lane.flags & engine.F_LPFAIL).any())
+    keeps = lane.keep_lists()
+    for i in range(0, n, n // sample):
+        o = orc.reduce(A[i], b[i])
+        assert keeps[i] == o['keep'] and int(lane.n_lp[i]) == o['n_lp']
+        assert abs(float(lane.r[i]) - o['r']) <= 1e-9

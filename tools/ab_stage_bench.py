@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B of library builds on the cfg2 reduce step: per-stage device times (CUDA events inside the
+"""A/B of library builds on a reduce step (cfg2, or AB_CFG="cfg,P,m,d"): per-stage device times (CUDA events inside the
 library) for every PB200_LIB given on the command line.  One process per library."""
 import json
 import os
@@ -12,7 +12,8 @@ if len(sys.argv) > 1 and sys.argv[1] == '--child':
     import torch
     import workloads as wl
     from polytope_b200 import engine
-    A, b = wl.box_cuts_batch(2, 10000, 32, 8)
+    cfg, P, m, d = [int(v) for v in os.environ.get('AB_CFG', '2,10000,32,8').split(',')]
+    A, b = wl.box_cuts_batch(cfg, P, m, d)
     A, b = torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda()
     for _ in range(3):
         res = engine.reduce_batch(A, b, want_A=False)

@@ -6,14 +6,27 @@ set -euo pipefail
 cd "$(dirname "$0")/../polytope_b200/csrc"
 mkdir -p ../ab
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-while [ $# -ge 2 ]; do
-    name=$1; flags=$2; shift 2
+# PB200_AB_ONLY="pb200" recompiles only those translation units per variant and links the others from
+# the objects of the last `make` (the flags must then only matter to the recompiled units); variants
+# are built in parallel.
+ONLY=${PB200_AB_ONLY:-"pb200 sets hull diff peak"}
+build_one() {
+    name=$1; flags=$2
     tmp=$(mktemp -d)
     for f in pb200 sets hull diff peak; do
-        nvcc -O3 -lineinfo -std=c++17 $ARCH -Xcompiler -fPIC $flags -c -o $tmp/$f.o $f.cu &
+        if [[ " $ONLY " == *" $f "* ]]; then
+            nvcc -O3 -lineinfo -std=c++17 $ARCH -Xcompiler -fPIC $flags -c -o $tmp/$f.o $f.cu &
+        else
+            cp $f.o $tmp/$f.o
+        fi
     done
     wait
     nvcc $ARCH -shared -o ../ab/$name.so $tmp/pb200.o $tmp/sets.o $tmp/hull.o $tmp/diff.o $tmp/peak.o
     rm -rf $tmp
     echo "built ab/$name.so  ($flags)"
+}
+while [ $# -ge 2 ]; do
+    build_one "$1" "$2" &
+    shift 2
 done
+wait
