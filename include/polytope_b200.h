@@ -58,6 +58,18 @@ int pb200_lp_batch(const double* G, const double* h, const double* c,
                    double* x, double* fun, int8_t* status, int32_t* iters,
                    void* stream);
 
+/* The same contract for LPs of any size: m unlimited, n <= 64 (one LP per CTA, G streamed through shared
+ * memory in chunks of 256 rows).  pb200_lp_batch covers m <= 128, n <= 32; this entry is what extreme()'s final
+ * is_fulldim(Q) (one row per vertex, polytope/polytope.py:1666-1670), intersections / envelopes of polytopes with
+ * many rows (:255-275, :1414-1464) and Chebyshev LPs of d >= 32 need.  The workspace holds the per-row iterates
+ * of the resident CTAs: pb200_lp_big_workspace_bytes(B, m, n) bytes.  shared_G != 0: G is ONE [m][n] matrix used by
+ * all B LPs (the row LPs of reduce(), :1142-1160, differ only in c and h). */
+size_t pb200_lp_big_workspace_bytes(int B, int m, int n);
+int pb200_lp_batch_big(const double* G, const double* h, const double* c,
+                       const int32_t* m_rows, int B, int m, int n, int shared_G,
+                       double* x, double* fun, int8_t* status, int32_t* iters,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Row normalisation of the Polytope constructor for P stacked polytopes.
  * Replaces: Polytope.__init__, polytope/polytope.py:128-138 (norm in numpy's
  * summation order, rows with norm <= 1e-10 dropped).

@@ -20,6 +20,8 @@ SIGNATURES = {
     'pb200_last_error': (c_char_p, []),
     'pb200_launch_count': (c_longlong, []),
     'pb200_lp_batch': (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 5),
+    'pb200_lp_big_workspace_bytes': (c_size_t, [c_int] * 3),
+    'pb200_lp_batch_big': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p] * 5 + [c_size_t, c_void_p]),
     'pb200_normalize_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p] * 4),
     'pb200_cheby_batch': (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p] * 4),
     'pb200_bbox_batch': (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_void_p] * 4),

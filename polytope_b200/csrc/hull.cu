@@ -12,12 +12,17 @@
 // (quickhull.py:168-190, :248-347) -- but makes every step a data-parallel sweep
 // of one CTA over a structure-of-arrays facet store:
 //
-//   * visibility is the point-to-hyperplane distance sweep over ALL live facets
-//     (quickhull.py:117-121 with the same `> abs_tol` rule) instead of a
-//     neighbour walk, so no neighbour lists exist at all;
-//   * the horizon is found by hashing the ridges (sorted (d-1)-tuples of vertex
-//     ids) of the visible facets: a ridge seen once is on the horizon -- this
-//     replaces `is_neighbor`;
+//   * every facet keeps D neighbour pointers (nbr[f][i] = the facet across the
+//     ridge that omits vertex i), so the visible set is the reference's own walk
+//     (quickhull.py:252-266) done level by level by the whole CTA: only the
+//     visible facets and their rim are touched (2 % of the facets at d = 12;
+//     round 1 swept every live facet per insertion -- 34 MB of DRAM traffic per
+//     hull for 2 MB of output);
+//   * the horizon is read off the pointers (a ridge of a visible facet whose
+//     neighbour is not visible); the cone's internal neighbours are found by
+//     hashing the ridges that contain the new point (sorted (d-2)-tuples of
+//     vertex ids): two new facets meet in each -- this replaces the O(|NV|^2 d^2)
+//     `is_neighbor` scan (quickhull.py:305-310);
 //   * facet hyperplanes come from a (d x d) Gauss-Jordan solve of V x = 1 held in
 //     the registers of a half warp (the reference solves the equivalent
 //     (d+1) x (d+1) system, quickhull.py:66-85), two facets per warp;
@@ -64,11 +69,15 @@ struct HullArgs {
 };
 
 struct HullWs {
-    double* nrm;      // [d][cap]
+    double* nrm;      // [cap][d]  (array of structures: a facet is touched as a whole)
     double* off;      // [cap]
-    int32_t* vid;     // [d][cap] sorted ascending per facet
+    int32_t* vid;     // [cap][d] sorted ascending per facet
+    int32_t* nbr;     // [cap][d] facet across the ridge that omits vertex i (-1: not wired)
     int32_t* state;   // [cap] 1 = live
-    uint8_t* vis;     // [cap]
+    int32_t* mark;    // [cap] visibility stamps of the insertions: 2 it + 2 visible, 2 it + 3 tested, not visible
+    int32_t* disc;    // [cap] claim of the walk (lowest discovering item), INT_MAX when idle
+    int32_t* ppos;    // [cap] per cone facet k: position of the new point in its sorted vertex list
+    int32_t* redo;    // [cap] cone facets whose pencil plane failed the check (rebuilt by Gauss-Jordan)
     int32_t* vis_list;  // [cap]
     int32_t* hor_list;  // [cap] ridge items f*d+i
     int32_t* new_list;  // [cap] slots of the new facets
@@ -92,9 +101,8 @@ __host__ __device__ inline size_t hull_ws_bytes(int Nmax, int d, int cap, int x_
     size_t s = 0;
     s += align_up(sizeof(double) * (size_t)d * cap);
     s += align_up(sizeof(double) * (size_t)cap);
-    s += align_up(sizeof(int32_t) * (size_t)d * cap);
-    s += align_up(sizeof(int32_t) * (size_t)cap);
-    s += align_up((size_t)cap);
+    s += 2 * align_up(sizeof(int32_t) * (size_t)d * cap);
+    s += 5 * align_up(sizeof(int32_t) * (size_t)cap);
     s += 4 * align_up(sizeof(int32_t) * (size_t)cap);
     s += align_up(sizeof(uint32_t) * (size_t)table_cap(cap, d));
     if (!x_in_smem) s += align_up(sizeof(double) * (size_t)d * Nmax);
@@ -108,8 +116,12 @@ __device__ inline HullWs hull_carve(char* p, int Nmax, int d, int cap, int x_in_
     w.nrm = (double*)take(sizeof(double) * (size_t)d * cap);
     w.off = (double*)take(sizeof(double) * (size_t)cap);
     w.vid = (int32_t*)take(sizeof(int32_t) * (size_t)d * cap);
+    w.nbr = (int32_t*)take(sizeof(int32_t) * (size_t)d * cap);
     w.state = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
-    w.vis = (uint8_t*)take((size_t)cap);
+    w.mark = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
+    w.disc = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
+    w.ppos = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
+    w.redo = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
     w.vis_list = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
     w.hor_list = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
     w.new_list = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
@@ -220,14 +232,22 @@ __device__ __forceinline__ void block_compact_range(BlockScratch& bs, int n, int
     }
 }
 
-// ---- ridge hashing ----
-__device__ __forceinline__ int ridge_elem(const int32_t* vid, int cap, int f, int i, int t) {
-    return vid[(size_t)(t + (t >= i ? 1 : 0)) * cap + f];
+// ---- ridges ----
+// element t of the ridge of facet f that omits vertex i
+__device__ __forceinline__ int ridge_elem(const int32_t* vid, int d, int f, int i, int t) {
+    return vid[(size_t)f * d + t + (t >= i ? 1 : 0)];
 }
-__device__ __forceinline__ uint32_t ridge_hash(const int32_t* vid, int cap, int d, int f, int i) {
+// element t of the (d-2)-tuple of facet f that omits the vertices at positions i and j
+__device__ __forceinline__ int cone_elem(const int32_t* vid, int d, int f, int i, int j, int t) {
+    const int lo = min(i, j), hi = max(i, j);
+    t += t >= lo ? 1 : 0;
+    t += t >= hi ? 1 : 0;
+    return vid[(size_t)f * d + t];
+}
+__device__ __forceinline__ uint32_t cone_hash(const int32_t* vid, int d, int f, int i, int j) {
     uint32_t h = 2166136261u;
-    for (int t = 0; t < d - 1; ++t) {
-        h ^= (uint32_t)ridge_elem(vid, cap, f, i, t);
+    for (int t = 0; t < d - 2; ++t) {
+        h ^= (uint32_t)cone_elem(vid, d, f, i, j, t);
         h *= 16777619u;
         h ^= h >> 13;
     }
@@ -235,12 +255,17 @@ __device__ __forceinline__ uint32_t ridge_hash(const int32_t* vid, int cap, int 
     h ^= h >> 16;
     return h;
 }
-__device__ __forceinline__ bool ridge_equal(const int32_t* vid, int cap, int d, int f, int i, int g, int j) {
-    for (int t = 0; t < d - 1; ++t)
-        if (ridge_elem(vid, cap, f, i, t) != ridge_elem(vid, cap, g, j, t)) return false;
+__device__ __forceinline__ bool cone_equal(const int32_t* vid, int d, int f, int i, int j, int g, int k, int l) {
+    for (int t = 0; t < d - 2; ++t)
+        if (cone_elem(vid, d, f, i, j, t) != cone_elem(vid, d, g, k, l, t)) return false;
     return true;
 }
-constexpr uint32_t DUP_BIT = 0x80000000u;
+// position of vertex id v in the sorted vertex list of facet f (v must be one of them)
+__device__ __forceinline__ int vertex_pos(const int32_t* vid, int d, int f, int v) {
+    int pos = 0;
+    for (int t = 0; t < d; ++t) pos += vid[(size_t)f * d + t] < v ? 1 : 0;
+    return pos;
+}
 
 // ---- facet hyperplane from its D vertices, one half warp per facet ----
 // Lane r (< D) of the group holds vertex id `myv` (sorted ascending over r).
@@ -308,7 +333,7 @@ __device__ __forceinline__ bool facet_plane(const double* __restrict__ X, int ld
 
 // builds the facets listed by `get_ids` (k -> lane's vertex id) into slots new_list[k]
 template <int D, class GetId>
-__device__ __forceinline__ bool make_facets(const HullWs& w, int cap, int ldx, int count, GetId get_id) {
+__device__ __forceinline__ bool make_facets(const HullWs& w, int cap, int ldx, int count, GetId get_id, const int32_t* klist = nullptr) {
     const int group = threadIdx.x >> 4, gl = threadIdx.x & 15;
     constexpr int NG = HT / 16;
     bool all_ok = true;
@@ -324,15 +349,15 @@ __device__ __forceinline__ bool make_facets(const HullWs& w, int cap, int ldx, i
         double off;
         const bool ok = facet_plane<D>(w.X, ldx, myv, gl, nk, mycol, off);
         if (act) {
-            const int g = w.new_list[k];
+            const int g = w.new_list[klist ? klist[k] : k];
             if (gl < D) {
-                w.vid[(size_t)gl * cap + g] = myv;
-                if (mycol >= 0) w.nrm[(size_t)mycol * cap + g] = nk[0];
+                w.vid[(size_t)g * D + gl] = myv;
+                w.nbr[(size_t)g * D + gl] = -1;
+                if (mycol >= 0) w.nrm[(size_t)g * D + mycol] = nk[0];
             }
             if (gl == 0) {
                 w.off[g] = off;
                 w.state[g] = 1;
-                w.vis[g] = 0;
             }
             all_ok = all_ok && ok;
         }
@@ -342,7 +367,8 @@ __device__ __forceinline__ bool make_facets(const HullWs& w, int cap, int ldx, i
 
 __device__ __forceinline__ double facet_dist(const HullWs& w, int cap, int d, int f, const double* p) {
     double acc = 0.0;
-    for (int k = 0; k < d; ++k) acc = fma(w.nrm[(size_t)k * cap + f], p[k], acc);
+    const double* nf = w.nrm + (size_t)f * d;
+    for (int k = 0; k < d; ++k) acc = fma(nf[k], p[k], acc);
     return acc - w.off[f];
 }
 
@@ -447,13 +473,19 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         w.X[(size_t)c * ldx + j] = P[e] - sh_c[c];
     }
     for (int j = tid; j < n; j += HT) { w.owner[j] = -1; w.odist[j] = 0.0; }
-    for (int f = tid; f < cap; f += HT) { w.state[f] = 0; w.vis[f] = 0; }
+    for (int f = tid; f < cap; f += HT) { w.state[f] = 0; w.mark[f] = 0; w.disc[f] = 0x7fffffff; }
     __syncthreads();
     if (tid <= d) w.owner[sh_simplex[tid]] = -2;
     if (tid <= d) w.new_list[tid] = tid;
     __syncthreads();
-    // initial facets: facet i omits simplex vertex i
+    // initial facets: facet i omits simplex vertex i; across the ridge that also omits simplex
+    // vertex j lies facet j
     bool ok = make_facets<D>(w, cap, ldx, d + 1, [&](int k, int gl) { return sh_simplex[gl + (gl >= k ? 1 : 0)]; });
+    __syncthreads();
+    for (int t = tid; t < (d + 1) * d; t += HT) {
+        const int i = t / d, idx = t - i * d;
+        w.nbr[(size_t)i * D + idx] = idx + (idx >= i ? 1 : 0);
+    }
     int hi = d + 1, nfree = 0, inserted = d + 1, created = d + 1;
     __syncthreads();
     // assign every other point to the first facet it is outside of (quickhull.py:226-246)
@@ -483,64 +515,54 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         int pstar;
         block_argmax(bs, bv, bi, ov, pstar);
         if (pstar < 0) break;
-        if (tid < d) sh_p[tid] = w.X[(size_t)tid * ldx + pstar];
-        if (tid == 0) w.owner[pstar] = -2;
+        const int f0 = w.owner[pstar];            // visible by construction (quickhull.py:256)
+        const int VIS = 2 * iter + 2, NOTVIS = 2 * iter + 3;
         __syncthreads();
-        // (b) visible facets: distance sweep over the whole facet store
+        if (tid < d) sh_p[tid] = w.X[(size_t)tid * ldx + pstar];
+        if (tid == 0) { w.owner[pstar] = -2; w.vis_list[0] = f0; w.mark[f0] = VIS; }
+        __syncthreads();
         double p[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) p[c] = sh_p[c];
-        int nV = 0;
-        block_compact_range(bs, hi, nV, parity,
-                            [&](int f) {
-                                // distance first, liveness second: no control dependence between the loads
-                                const double dist = facet_dist(w, cap, d, f, p);
-                                const bool v = (dist > a.tol) & (w.state[f] == 1);
-                                w.vis[f] = v ? 1 : 0;
-                                return v;
-                            },
-                            [&](int pos, int f) { w.vis_list[pos] = f; });
-        __syncthreads();
-        // (c) horizon: ridges of visible facets that occur once
-        const unsigned tcap = table_cap(cap, d);
-        unsigned tsize = 1024;
-        while (tsize < 2u * (unsigned)nV * (unsigned)d) tsize <<= 1;
-        if (tsize > tcap) tsize = tcap;
-        for (unsigned e = tid; e < tsize; e += HT) w.table[e] = 0;
-        __syncthreads();
-        const int items = nV * d;
-        for (int t = tid; t < items; t += HT) {
-            const int f = w.vis_list[t / d], i = t % d;
-            uint32_t slot = ridge_hash(w.vid, cap, d, f, i) & (tsize - 1);
-            const uint32_t me = (uint32_t)(f * d + i) + 1u;
-            for (unsigned probe = 0; probe < tsize; ++probe) {
-                uint32_t cur = atomicCAS(w.table + slot, 0u, me);
-                if (cur == 0u) break;
-                const uint32_t other = (cur & ~DUP_BIT) - 1u;
-                if (ridge_equal(w.vid, cap, d, f, i, (int)(other / d), (int)(other % d))) {
-                    atomicOr(w.table + slot, DUP_BIT);
-                    break;
-                }
-                slot = (slot + 1) & (tsize - 1);
+        // (b) visible facets: the neighbour walk of quickhull.py:252-266, one level per round.  A facet
+        // reached from several sides is claimed by the lowest item (atomicMin), so the order of vis_list
+        // -- and with it the order of the cone -- does not depend on thread timing.
+        int nV = 1, lo = 0;
+        while (lo < nV) {
+            const int items = (nV - lo) * d;
+            for (int t = tid; t < items; t += HT) {
+                const int f = w.vis_list[lo + t / d], i = t % d;
+                const int g = w.nbr[(size_t)f * D + i];
+                if (g < 0) { ok = false; continue; }
+                const int mk = w.mark[g];
+                if (mk == VIS || mk == NOTVIS) continue;
+                if (facet_dist(w, cap, d, g, p) > a.tol) atomicMin(w.disc + g, t);
+                else w.mark[g] = NOTVIS;
             }
+            __syncthreads();
+            int nNew = nV;
+            block_compact_range(bs, items, nNew, parity,
+                                [&](int t) {
+                                    const int g = w.nbr[(size_t)w.vis_list[lo + t / d] * D + t % d];
+                                    return g >= 0 && w.disc[g] == t;
+                                },
+                                [&](int pos, int t) {
+                                    const int g = w.nbr[(size_t)w.vis_list[lo + t / d] * D + t % d];
+                                    w.vis_list[pos] = g;
+                                    w.mark[g] = VIS;
+                                    w.disc[g] = 0x7fffffff;
+                                });
+            __syncthreads();
+            lo = nV;
+            nV = nNew;
         }
-        __syncthreads();
+        // (c) horizon: ridges of visible facets whose neighbour is not visible
+        const int items = nV * d;
         int nH = 0;
         block_compact_range(bs, items, nH, parity,
                             [&](int t) {
-                                const int f = w.vis_list[t / d], i = t % d;
-                                const int item = f * d + i;
-                                uint32_t slot = ridge_hash(w.vid, cap, d, f, i) & (tsize - 1);
-                                for (unsigned probe = 0; probe < tsize; ++probe) {
-                                    const uint32_t cur = w.table[slot];
-                                    if (cur == 0u) break;
-                                    const uint32_t other = (cur & ~DUP_BIT) - 1u;
-                                    if (other == (uint32_t)item ||
-                                        ridge_equal(w.vid, cap, d, f, i, (int)(other / d), (int)(other % d)))
-                                        return !(cur & DUP_BIT);
-                                    slot = (slot + 1) & (tsize - 1);
-                                }
-                                return false;
+                                const int g = w.nbr[(size_t)w.vis_list[t / d] * D + t % d];
+                                return g >= 0 && w.mark[g] != VIS;
                             },
                             [&](int pos, int t) {
                                 if (pos < cap) w.hor_list[pos] = w.vis_list[t / d] * d + t % d;
@@ -551,28 +573,146 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         const int fresh = nH - from_free;
         if (hi + fresh > cap || nH > cap) { status = HS_FACET_CAP; break; }
         for (int k = tid; k < nH; k += HT) w.new_list[k] = k < from_free ? w.free_stack[nfree - 1 - k] : hi + (k - from_free);
+        const unsigned tcap = table_cap(cap, d);
+        unsigned tsize = 1024;
+        while (tsize < 2u * (unsigned)nH * (unsigned)d) tsize <<= 1;
+        if (tsize > tcap) tsize = tcap;
+        for (unsigned e = tid; e < tsize; e += HT) w.table[e] = 0;
         __syncthreads();
-        // (e) new facets = horizon ridge + the new point
-        ok = make_facets<D>(w, cap, ldx, nH, [&](int k, int gl) {
-            const int item = w.hor_list[k];
-            const int f = item / d, i = item - f * d;
-            // lane t < d-1 of the half warp fetches element t of the sorted ridge; pstar is
-            // merged in at its sorted position with one ballot and one shuffle
-            const int e = gl < d - 1 ? ridge_elem(w.vid, cap, f, i, gl) : 0x7fffffff;
-            const unsigned less = __ballot_sync(FULL, e < pstar);
-            const int pos = __popc((less >> (threadIdx.x & 16)) & 0xffffu);
-            const int src = gl < pos ? gl : gl - 1;
-            const int other = __shfl_sync(FULL, e, src < 0 ? 0 : src, 16);
-            return gl == pos ? pstar : other;
-        }) && ok;
+        // (e) new facets = horizon ridge + the new point, one thread per facet.  The hyperplanes through the
+        // ridge form a pencil spanned by the planes of the two facets that meet in it (the visible one and the
+        // one outside), so the plane through pstar is  dist_out(p) (n_f, off_f) - dist_f(p) (n_out, off_out):
+        // O(d) instead of the d x d solve.  The result is checked against the facet's own vertices
+        // (|n . v - off| <= 1e-13 max(1, |n|.|v|) for all d of them, so no error is inherited from the parent planes); a facet
+        // that fails -- nearly coplanar parents -- is rebuilt from its vertices by Gauss-Jordan below.
+        int nRedo = 0;
+        {
+            for (int k0 = 0; k0 < nH; k0 += HT) {
+                const int k = k0 + tid;
+                bool bad = false;
+                if (k < nH) {
+                    const int item = w.hor_list[k];
+                    const int f = item / d, i = item - f * d;
+                    const int gout = w.nbr[(size_t)f * D + i];
+                    const int g = w.new_list[k];
+                    int vv[D];
+                    int pos = 0;
+#pragma unroll
+                    for (int t = 0; t < D - 1; ++t) {
+                        const int e = ridge_elem(w.vid, d, f, i, t);
+                        pos += e < pstar ? 1 : 0;
+                        vv[t] = e;
+                    }
+                    const double* nf = w.nrm + (size_t)f * D;
+                    const double* ng = w.nrm + (size_t)gout * D;
+                    double af[D], ag[D];
+                    double df = -w.off[f], dg = -w.off[gout];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        af[c] = nf[c];
+                        ag[c] = ng[c];
+                        df = fma(af[c], p[c], df);
+                        dg = fma(ag[c], p[c], dg);
+                    }
+                    double nn[D];
+                    double n2 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        nn[c] = dg * af[c] - df * ag[c];
+                        n2 = fma(nn[c], nn[c], n2);
+                    }
+                    double off = dg * w.off[f] - df * w.off[gout];
+                    // outward: the shifted origin is strictly inside, so the offset must come out positive
+                    const double sc = (off < 0.0 ? -1.0 : 1.0) / sqrt(n2);
+                    off *= sc;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) nn[c] *= sc;
+                    double worst = 0.0, mag = 1.0;
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        const int v = t < D - 1 ? vv[t] : pstar;
+                        double acc = -off, ab = 0.0;
+#pragma unroll
+                        for (int c = 0; c < D; ++c) {
+                            const double xv = w.X[(size_t)c * ldx + v];
+                            acc = fma(nn[c], xv, acc);
+                            ab = fma(fabs(nn[c]), fabs(xv), ab);
+                        }
+                        worst = fmax(worst, fabs(acc));
+                        mag = fmax(mag, ab);
+                    }
+                    bad = !(worst <= 1e-13 * mag) || !(off > 0.0) || !(n2 > 0.0);
+                    // sorted vertex list with pstar merged in
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        const int src = t < pos ? t : t - 1;
+                        int e = pstar;
+#pragma unroll
+                        for (int u = 0; u < D - 1; ++u)
+                            if (u == src && t != pos) e = vv[u];
+                        w.vid[(size_t)g * D + t] = e;
+                        w.nbr[(size_t)g * D + t] = -1;
+                        w.nrm[(size_t)g * D + t] = nn[t];
+                    }
+                    w.off[g] = off;
+                    w.state[g] = 1;
+                    w.ppos[k] = pos;
+                }
+                const int at = block_compact_pos(bs, bad, nRedo, parity);
+                if (bad) w.redo[at] = k;
+            }
+        }
         __syncthreads();
+        if (nRedo > 0) {
+            ok = make_facets<D>(w, cap, ldx, nRedo, [&](int q, int gl) {
+                const int k = w.redo[q];
+                return gl < d ? w.vid[(size_t)w.new_list[k] * D + gl] : 0;
+            }, w.redo) && ok;
+            __syncthreads();
+        }
+        // (measured r02t / r02u, 1000 cfg4 duals: one thread per new FACET with the vertex row in registers 75 ms,
+        // the ridge table in shared memory 38 ms -- 64 KB per CTA cost more L1 than the faster atomics gained --
+        // against 28 ms for this form: one thread per (facet, ridge), table in global memory)
+        // (e2) neighbour pointers of the cone.  Across the horizon ridge (the one that omits pstar): the
+        // facet outside, whose own pointer moves from the visible facet to the new one.  Across the d - 1
+        // ridges that contain pstar: another new facet, found by hashing the ridge without pstar -- the first
+        // of the two inserts itself, the second wires both (quickhull.py:305-310).
+        for (int t = tid; t < nH * d; t += HT) {
+            const int k = t / d, i = t - k * d;
+            const int g = w.new_list[k];
+            const int pos = w.ppos[k];
+            if (i == pos) {
+                const int item = w.hor_list[k];
+                const int f = item / d;
+                const int gout = w.nbr[(size_t)f * D + (item - f * d)];
+                w.nbr[(size_t)g * D + pos] = gout;
+                for (int j = 0; j < d; ++j)
+                    if (w.nbr[(size_t)gout * D + j] == f) w.nbr[(size_t)gout * D + j] = g;
+                continue;
+            }
+            uint32_t slot = cone_hash(w.vid, d, g, i, pos) & (tsize - 1);
+            const uint32_t me = (uint32_t)t + 1u;
+            for (unsigned probe = 0; probe < tsize; ++probe) {
+                const uint32_t cur = atomicCAS(w.table + slot, 0u, me);
+                if (cur == 0u) break;
+                const int t2 = (int)(cur - 1u);
+                const int k2 = t2 / d, i2 = t2 - k2 * d;
+                const int g2 = w.new_list[k2];
+                if (cone_equal(w.vid, d, g, i, pos, g2, i2, w.ppos[k2])) {
+                    w.nbr[(size_t)g * D + i] = g2;
+                    w.nbr[(size_t)g2 * D + i2] = g;
+                    break;
+                }
+                slot = (slot + 1) & (tsize - 1);
+            }
+        }
         // (f) orphaned outside points go to the first new facet (in cone order) they are
         // outside of (quickhull.py:316-336): all (facet, orphan) pairs in parallel
         int nO = 0;
         block_compact_range(bs, n, nO, parity,
                             [&](int j) {
                                 const int o = w.owner[j];
-                                return o >= 0 && w.vis[o] != 0;
+                                return o >= 0 && w.mark[o] == VIS;
                             },
                             [&](int pos, int j) { w.orph[pos] = j; w.cand[j] = 0x7fffffff; });
         __syncthreads();
@@ -605,7 +745,6 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         for (int k = tid; k < nV; k += HT) {
             const int f = w.vis_list[k];
             w.state[f] = 0;
-            w.vis[f] = 0;
             w.free_stack[nfree - from_free + k] = f;
         }
         nfree = nfree - from_free + nV;
@@ -614,6 +753,8 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         created += nH;
         __syncthreads();
     }
+    // a singular facet system or an unwired ridge seen by any thread fails the whole hull
+    ok = !__syncthreads_or(ok ? 0 : 1);
     if (status == HS_OK && !ok) status = HS_SINGULAR;
     if (status != HS_OK) { finish(status, 0, 0, inserted, created); return; }
 
@@ -633,15 +774,15 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
     for (long long e = tid; e < (long long)nF * d; e += HT) {
         const int k = (int)(e / d), c = (int)(e - (long long)k * d);
         const int f = w.vis_list[k];
-        a.outA[(size_t)o * d + e] = w.nrm[(size_t)c * cap + f];
-        const int v = w.vid[(size_t)c * cap + f];
+        a.outA[(size_t)o * d + e] = w.nrm[(size_t)f * D + c];
+        const int v = w.vid[(size_t)f * D + c];
         a.outV[(size_t)o * d + e] = v;
         if (a.is_vertex) a.is_vertex[(size_t)h * Nmax + v] = 1;
     }
     for (int k = tid; k < nF; k += HT) {
         const int f = w.vis_list[k];
         double dot = 0.0;
-        for (int c = 0; c < d; ++c) dot = fma(w.nrm[(size_t)c * cap + f], sh_c[c], dot);
+        for (int c = 0; c < d; ++c) dot = fma(w.nrm[(size_t)f * D + c], sh_c[c], dot);
         a.outb[o + k] = w.off[f] + dot;
     }
     finish(HS_OK, nF, o, inserted, created);

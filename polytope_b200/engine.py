@@ -56,26 +56,45 @@ def _out(host, *tensors):
     return tuple(t.cpu().numpy() for t in tensors)
 
 
+LP_MAX_M, LP_MAX_N = 128, 32          # envelope of pb200_lp_batch (lane / warp kernels)
+LP_BIG_MAX_N = 64                      # pb200_lp_batch_big
+
+
 def lp_batch(C, G, H, m_rows=None):
     """B independent LPs min c'x s.t. Gx <= h (solvers.lpsolve, one per row of the batch).
 
-    C[B,n], G[B,m,n], H[B,m] -> status[B] int8, X[B,n], fun[B], iters[B] int32.
+    C[B,n], G[B,m,n] (or G[m,n]: one matrix shared by all B LPs), H[B,m]
+    -> status[B] int8, X[B,n], fun[B], iters[B] int32.
+    LPs with more than 128 rows or 32 columns (or a shared G) take the one-LP-per-CTA solver.
     """
     _require_cuda()
     lib = _capi.lib()
     G, host = _dev(G)
     C, _ = _dev(C)
     H, _ = _dev(H)
-    B, m, n = G.shape
-    assert C.shape == (B, n) and H.shape == (B, m), (C.shape, G.shape, H.shape)
+    shared = G.dim() == 2
+    B = C.shape[0]
+    m, n = G.shape[-2:]
+    assert C.shape == (B, n) and H.shape == (B, m) and (shared or G.shape[0] == B), (C.shape, G.shape, H.shape)
     mr, mr_ptr = _opt(m_rows, torch.int32)
     X = torch.empty((B, n), dtype=torch.float64, device='cuda')
     fun = torch.empty(B, dtype=torch.float64, device='cuda')
     status = torch.empty(B, dtype=torch.int8, device='cuda')
     iters = torch.empty(B, dtype=torch.int32, device='cuda')
-    _capi.check(lib.pb200_lp_batch(G.data_ptr(), H.data_ptr(), C.data_ptr(), mr_ptr, B, m, n,
-                                   X.data_ptr(), fun.data_ptr(), status.data_ptr(),
-                                   iters.data_ptr(), _stream()), 'pb200_lp_batch')
+    if shared or m > LP_MAX_M or n > LP_MAX_N:
+        if n > LP_BIG_MAX_N:
+            raise _capi.Pb200Error('lp_batch: at most %d columns, got %d' % (LP_BIG_MAX_N, n))
+        nbytes = int(lib.pb200_lp_big_workspace_bytes(B, m, n))
+        if B and not nbytes:
+            raise _capi.Pb200Error('pb200_lp_big_workspace_bytes: unsupported sizes (m=%d, n=%d)' % (m, n))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device='cuda')
+        _capi.check(lib.pb200_lp_batch_big(G.data_ptr(), H.data_ptr(), C.data_ptr(), mr_ptr, B, m, n, int(shared),
+                                           X.data_ptr(), fun.data_ptr(), status.data_ptr(), iters.data_ptr(),
+                                           ws.data_ptr(), nbytes, _stream()), 'pb200_lp_batch_big')
+    else:
+        _capi.check(lib.pb200_lp_batch(G.data_ptr(), H.data_ptr(), C.data_ptr(), mr_ptr, B, m, n,
+                                       X.data_ptr(), fun.data_ptr(), status.data_ptr(),
+                                       iters.data_ptr(), _stream()), 'pb200_lp_batch')
     return _out(host, status, X, fun, iters)
 
 

@@ -130,7 +130,89 @@ def test_lp_batch_device_tensors_stay_on_device():
 
 def test_unsupported_sizes_fail_loudly():
     from polytope_b200 import solvers, _capi
-    with pytest.raises(_capi.Pb200Error):
-        solvers.lpsolve_batch(np.zeros((1, 40)), np.zeros((1, 4, 40)), np.zeros((1, 4)))
-    with pytest.raises(_capi.Pb200Error):
-        solvers.lpsolve_batch(np.zeros((1, 2)), np.zeros((1, 200, 2)), np.zeros((1, 200)))
+    with pytest.raises(_capi.Pb200Error):        # more than 64 columns: no kernel takes it, and nothing falls back
+        solvers.lpsolve_batch(np.zeros((1, 70)), np.zeros((1, 4, 70)), np.zeros((1, 4)))
+    # 40 columns / 200 rows used to be refused; they now go to the one-LP-per-CTA solver
+    st, X, fun = solvers.lpsolve_batch(np.ones((1, 2)), np.vstack([-np.eye(2)] * 100)[None], np.ones((1, 200)))
+    assert st[0] == 0 and abs(fun[0] + 2.0) < 1e-12
+
+
+def _random_big_lps(rng, count, m_lo, m_hi, n_lo, n_hi):
+    from scipy import optimize
+    lps = []
+    for k in range(count):
+        n = int(rng.integers(n_lo, n_hi + 1))
+        m = int(rng.integers(m_lo, m_hi + 1))
+        G = rng.standard_normal((m, n))
+        kind = k % 5
+        if kind == 1:
+            G[:, -1] = G[:, 0]                 # rank deficient
+        if kind == 2:
+            G[1] = -G[0]                       # infeasible pair
+        h = rng.uniform(0.1, 2.0, m)
+        if kind == 2:
+            h[1] = -h[0] - 1.0
+        if kind in (0, 3):                     # bounded: a box around the origin plus cuts
+            G = np.vstack([np.eye(n), -np.eye(n), G])
+            h = np.hstack([np.ones(2 * n), h])
+        c = rng.standard_normal(n)
+        sol = optimize.linprog(c, G, h, bounds=(None, None))
+        if sol.status in (0, 2, 3):
+            lps.append((c, G, h, sol.status, sol.fun if sol.status == 0 else np.nan))
+    return lps
+
+
+@pytest.mark.parametrize('m_lo,m_hi,n_lo,n_hi', [(130, 700, 2, 16), (40, 300, 33, 64), (1500, 4000, 5, 13)])
+def test_big_lps_one_per_cta_against_highs(m_lo, m_hi, n_lo, n_hi):
+    """pb200_lp_batch_big: LPs beyond 128 rows / 32 columns (every status) against scipy/HiGHS, one call per LP
+    shape and ragged batches through m_rows."""
+    from polytope_b200 import engine
+    rng = np.random.default_rng(m_lo + n_hi)
+    lps = _random_big_lps(rng, 30, m_lo, m_hi, n_lo, n_hi)
+    assert {0, 2, 3} <= set(lp[3] for lp in lps)
+    by_n = {}
+    for lp in lps:
+        by_n.setdefault(len(lp[0]), []).append(lp)
+    for n, group in by_n.items():
+        m = max(len(lp[2]) for lp in group)
+        B = len(group)
+        G = np.zeros((B, m, n))
+        H = np.zeros((B, m))
+        C = np.zeros((B, n))
+        rows = np.zeros(B, dtype=np.int32)
+        for k, (c, g, h, _, _) in enumerate(group):
+            G[k, :len(h)] = g
+            H[k, :len(h)] = h
+            C[k] = c
+            rows[k] = len(h)
+        if m <= engine.LP_MAX_M and n <= engine.LP_MAX_N:      # keep the shape on the big path
+            pad = engine.LP_MAX_M + 1 - m
+            G = np.concatenate([G, np.zeros((B, pad, n))], 1)
+            H = np.concatenate([H, np.ones((B, pad))], 1)
+        status, X, fun, iters = engine.lp_batch(C, G, H, rows)
+        ref_st = np.array([lp[3] for lp in group])
+        ref_fun = np.array([lp[4] for lp in group])
+        assert np.array_equal(status, ref_st), (n, status, ref_st)
+        ok = ref_st == 0
+        assert np.all(np.abs(fun[ok] - ref_fun[ok]) <= 1e-7 + 1e-7 * np.abs(ref_fun[ok])), np.abs(fun[ok] - ref_fun[ok]).max()
+        for k in np.nonzero(ok)[0]:
+            mk = rows[k]
+            assert np.all(G[k, :mk] @ X[k] <= H[k, :mk] + 1e-9 * (1 + np.abs(H[k, :mk])))
+
+
+def test_big_lps_with_a_shared_constraint_matrix():
+    """G[m, n] shared by all LPs of the call (the row LPs of a reduce() with many rows)."""
+    from scipy import optimize
+    from polytope_b200 import engine
+    rng = np.random.default_rng(3)
+    n, m, B = 7, 300, 40
+    G = np.vstack([np.eye(n), -np.eye(n), rng.standard_normal((m - 2 * n, n))])
+    h = np.hstack([np.ones(2 * n), rng.uniform(0.3, 1.5, m - 2 * n)])
+    C = rng.standard_normal((B, n))
+    H = np.tile(h, (B, 1))
+    H[np.arange(B), np.arange(B)] += 0.1
+    status, X, fun, iters = engine.lp_batch(C, G, H)
+    for k in range(B):
+        sol = optimize.linprog(C[k], G, H[k], bounds=(None, None))
+        assert status[k] == sol.status == 0
+        assert abs(fun[k] - sol.fun) <= 1e-9 * (1 + abs(sol.fun))

@@ -9,11 +9,11 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 # PB200_AB_ONLY="pb200" recompiles only those translation units per variant and links the others from
 # the objects of the last `make` (the flags must then only matter to the recompiled units); variants
 # are built in parallel.
-ONLY=${PB200_AB_ONLY:-"pb200 sets hull diff peak"}
+ONLY=${PB200_AB_ONLY:-"pb200 sets hull diff peak lp_cta"}
 build_one() {
     name=$1; flags=$2
     tmp=$(mktemp -d)
-    for f in pb200 sets hull diff peak; do
+    for f in pb200 sets hull diff peak lp_cta; do
         if [[ " $ONLY " == *" $f "* ]]; then
             nvcc -O3 -lineinfo -std=c++17 $ARCH -Xcompiler -fPIC $flags -c -o $tmp/$f.o $f.cu &
         else
@@ -21,7 +21,7 @@ build_one() {
         fi
     done
     wait
-    nvcc $ARCH -shared -o ../ab/$name.so $tmp/pb200.o $tmp/sets.o $tmp/hull.o $tmp/diff.o $tmp/peak.o
+    nvcc $ARCH -shared -o ../ab/$name.so $tmp/pb200.o $tmp/sets.o $tmp/hull.o $tmp/diff.o $tmp/peak.o $tmp/lp_cta.o
     rm -rf $tmp
     echo "built ab/$name.so  ($flags)"
 }
