@@ -122,6 +122,15 @@ def cheby_batch(A, b, m_rows=None, rows=None):
     A, host = _dev(A)
     b, _ = _dev(b)
     P, m, d = A.shape
+    if m > LP_MAX_M or d + 1 > LP_MAX_N:
+        # beyond the lane / warp kernels: the LP of polytope.py:1280-1300 assembled here, solved one per CTA
+        if rows is not None:
+            raise _capi.Pb200Error('cheby_batch: row masks need m <= 64')
+        G = torch.cat([A, torch.sqrt((A * A).sum(-1, keepdim=True))], -1).contiguous()
+        C = torch.zeros((P, d + 1), dtype=torch.float64, device='cuda')
+        C[:, d] = -1.0
+        status, X, _, _ = lp_batch(C, G, b, _dev(m_rows)[0] if m_rows is not None else None)
+        return _out(host, X[:, d].contiguous(), X[:, :d].contiguous(), status)
     mr, mr_ptr = _opt(m_rows, torch.int32)
     rw, rw_ptr = _opt(rows, torch.int64)
     r = torch.empty(P, dtype=torch.float64, device='cuda')
@@ -140,6 +149,25 @@ def bbox_batch(A, b, m_rows=None):
     A, host = _dev(A)
     b, _ = _dev(b)
     P, m, d = A.shape
+    if m > LP_MAX_M or d > LP_MAX_N:
+        # beyond the lane / warp kernels: 2 d passes of the one-LP-per-CTA solver (every pass one objective for all
+        # P polytopes), then the status conventions of polytope.py:1372-1402
+        mrd = _dev(m_rows)[0] if m_rows is not None else None
+        inf, nan = float('inf'), float('nan')
+        lo = torch.empty((P, d), dtype=torch.float64, device='cuda')
+        hi = torch.empty((P, d), dtype=torch.float64, device='cuda')
+        status = torch.empty((P, 2 * d), dtype=torch.int8, device='cuda')
+        for q in range(2 * d):
+            j = q % d
+            C = torch.zeros((P, d), dtype=torch.float64, device='cuda')
+            C[:, j] = 1.0 if q < d else -1.0
+            st, X, _, _ = lp_batch(C, A, b, mrd)
+            status[:, q] = st
+            (lo if q < d else hi)[:, j] = X[:, j]
+        sl, su = status[:, :d], status[:, d:]
+        lo = torch.where(sl == 3, -inf, torch.where(sl == 2, 0.0, torch.where(sl == 0, lo, nan)))
+        hi = torch.where(su == 3, inf, torch.where(su == 2, lo, torch.where(su == 0, hi, nan)))
+        return _out(host, lo, hi, status)
     mr, mr_ptr = _opt(m_rows, torch.int32)
     lo = torch.empty((P, d), dtype=torch.float64, device='cuda')
     hi = torch.empty((P, d), dtype=torch.float64, device='cuda')

@@ -431,6 +431,60 @@ def bounding_box_batch(polys):
     return [p.bbox for p in polys]
 
 
+REDUCE_MAX_ROWS, REDUCE_MAX_DIM = 64, 31      # envelope of pb200_reduce_batch (row sets are 64-bit masks)
+
+
+def _reduce_wide(poly, nonEmptyBounded, abs_tol):
+    """reduce() of one polytope outside the envelope of the fused device pipeline (more than 64 rows or 31
+    columns).  The steps of polytope.py:1081-1163 on the host, every LP on the device: the Chebyshev LP of
+    is_fulldim, the 2 d bounding-box LPs, then ALL row LPs in one call that shares G (one LP per CTA for LPs
+    of more than 128 rows).  The in-place `h[k] += 0.1 ... h[k] -= 0.1` of the reference leaves rows before k
+    one rounding away from b (:1147-1149); the right-hand sides below carry exactly that."""
+    if not is_fulldim(poly):
+        return Polytope()
+    keep_row = np.nonzero(poly.b != np.inf)
+    A_arr, b_arr = poly.A[keep_row], poly.b[keep_row]
+    neq = A_arr.shape[0]
+    a_norm = 1 / np.sqrt(np.sum(A_arr.T**2, 0))
+    a_normed = np.dot(A_arr.T, np.diag(a_norm)).T
+    # candidate pairs from one matrix product, each confirmed by the reference's own 1-D np.dot (:1102)
+    close = np.triu(a_normed.dot(a_normed.T) > 1 - abs_tol - 1e-9, 1)
+    remove_row = []
+    for i, j in zip(*np.nonzero(close)):
+        if np.dot(a_normed[i].T, a_normed[j]) > 1 - abs_tol:
+            remove_row.append(j if b_arr[i] * a_norm[i] < b_arr[j] * a_norm[j] else i)
+    keep_row = np.setdiff1d(range(neq), remove_row).tolist()
+    A_arr, b_arr = A_arr[keep_row], b_arr[keep_row]
+    neq, nx = A_arr.shape
+    if nonEmptyBounded and neq <= nx + 1:
+        return Polytope(A_arr, b_arr)
+    if neq > 3 * nx:
+        lb, ub = Polytope(A_arr, b_arr).bounding_box
+        cand = ~ (np.dot((A_arr > 0) * A_arr, ub - lb) - (np.array([b_arr]).T - np.dot(A_arr, lb)) < -1e-4)
+        A_arr, b_arr = A_arr[cand.squeeze()], b_arr[cand.squeeze()]
+    neq, nx = A_arr.shape
+    if nonEmptyBounded and neq <= nx + 1:
+        return Polytope(A_arr, b_arr)
+    A_arr = np.ascontiguousarray(A_arr)
+    drift = (b_arr + 0.1) - 0.1
+    keep_row = []
+    chunk = max(1, (64 << 20) // (8 * neq))           # right-hand sides of one call: <= 64 MB
+    for k0 in range(0, neq, chunk):
+        ks = np.arange(k0, min(neq, k0 + chunk))
+        H = np.where(np.arange(neq)[None, :] < ks[:, None], drift[None, :], b_arr[None, :])
+        H[np.arange(len(ks)), ks] = b_arr[ks] + 0.1
+        status, _, fun, _ = engine.lp_batch(-A_arr[ks], A_arr, H)
+        for t, k in enumerate(ks):
+            if status[t] == 0:
+                if -fun[t] - drift[k] > abs_tol:
+                    keep_row.append(int(k))
+            elif status[t] == 3:
+                keep_row.append(int(k))
+    polyOut = Polytope(A_arr[keep_row], drift[keep_row])
+    polyOut.minrep = True
+    return polyOut
+
+
 def reduce_batch(polys, abs_tol=ABS_TOL, nonEmptyBounded=1):
     """[reduce(p, nonEmptyBounded, abs_tol) for p in polys] through the device pipeline."""
     out = [None] * len(polys)
@@ -442,6 +496,8 @@ def reduce_batch(polys, abs_tol=ABS_TOL, nonEmptyBounded=1):
             out[k] = p
         elif p.fulldim is False or is_empty(p):
             out[k] = Polytope()
+        elif p.A.shape[0] > REDUCE_MAX_ROWS or p.A.shape[1] > REDUCE_MAX_DIM:
+            out[k] = _reduce_wide(p, nonEmptyBounded, abs_tol)
         else:
             todo.append(k)
     if todo:
@@ -596,9 +652,18 @@ def adjacency_matrix(cells, abs_tol=ABS_TOL):
     adj = np.eye(n, dtype=np.int8)
     if n < 2:
         return adj
+    i, j = np.tril_indices(n, -1)
+    if max(c.A.shape[0] for c in cells) > 32:
+        # cells with more rows than the pair kernel stacks (2 x 32): the stacked polytopes of is_adjacent
+        # (polytope.py:1856-1866) built here, one batch of Chebyshev LPs
+        pairs = [Polytope(np.vstack([cells[a].A, cells[c].A]), np.hstack([cells[a].b, cells[c].b]) + abs_tol)
+                 for a, c in zip(i, j)]
+        flags = np.array([rc > abs_tol / 10 for rc, _ in cheby_ball_batch(pairs)], dtype=np.int8)
+        adj[i, j] = flags
+        adj[j, i] = flags
+        return adj
     A, b, _ = _stack(cells)
     flags, _, _ = engine.adjacent_pairs(A, b, abs_tol=abs_tol)
-    i, j = np.tril_indices(n, -1)
     adj[i, j] = flags
     adj[j, i] = flags
     return adj
@@ -1076,9 +1141,16 @@ def region_diff_batch(polys, regs, abs_tol=ABS_TOL, intersect_tol=ABS_TOL):
     reduced = {}
     if len(red_idx):
         mx = int(res.rows[red_idx].max())          # the pool is padded to piece_m rows
-        rr = engine.reduce_batch(np.ascontiguousarray(res.A[red_idx][:, :mx]), np.ascontiguousarray(res.b[red_idx][:, :mx]),
-                                 res.rows[red_idx], normalize=True)
-        keeps = rr.keep_lists()
+        if mx > REDUCE_MAX_ROWS:
+            # pieces with more rows than the fused pipeline's row masks hold: reduce() object by object
+            pieces = [Polytope(res.A[f][:res.rows[f]], res.b[f][:res.rows[f]]) for f in red_idx]
+            for f, q in zip(red_idx, reduce_batch(pieces)):
+                reduced[f] = q
+            red_idx = []
+        else:
+            rr = engine.reduce_batch(np.ascontiguousarray(res.A[red_idx][:, :mx]), np.ascontiguousarray(res.b[red_idx][:, :mx]),
+                                     res.rows[red_idx], normalize=True)
+            keeps = rr.keep_lists()
         for t, f in enumerate(red_idx):
             if rr.flags[t] & engine.F_EMPTY:
                 reduced[f] = Polytope()
