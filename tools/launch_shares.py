@@ -19,7 +19,7 @@ for r in rows[1:]:
 own = {k: v for k, v in agg.items() if 'pb200' in k or 'lane_kernel' in k or 'lane_own' in k}
 import re
 # kernels of bench.py's untimed extras (cfg4 extreme(), cfg5 pair flags, the DFMA peak measurement), not of the cfg2 step
-extras = re.compile(r'hull_kernel|lp_kernel<2|AdjacentOwn|dual_|dfma_peak|sweep_kernel|<1[026],')
+extras = re.compile(r'hull_kernel|lp_kernel<2|AdjacentOwn|dual_|dfma_peak|sweep_kernel|<1[026],|lane_kernel<1[26]')
 step = {k: v for k, v in own.items() if not extras.search(k)}
 tot = sum(s for _, s in step.values())
 print('# launch shares from %s (ncu --metrics gpu__time_duration.sum --clock-control none; per-launch times are' % sys.argv[1])

@@ -6,7 +6,7 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 for tool in memcheck racecheck; do
-    for fam in lp_small lp_generic diff hull sets; do
+    for fam in lp_small lp_generic lp_lane lp_cta diff hull sets; do
         log=gpurun_out/sanitize_${tool}_${fam}.log
         timeout 900 compute-sanitizer --tool $tool --print-limit 20 --log-file $log \
             python tools/sanitize_driver.py $fam > gpurun_out/sanitize_${tool}_${fam}.out 2>&1
