@@ -262,12 +262,13 @@ def run_gpu(args):
     def step_e2e():
         # the public host-buffer call: pinned (A, b) in, masks / flags / counts out.  N = 1: the H2D
         # and D2H copies happen inside (chunked over two streams, overlapping the kernels), results
-        # are numpy arrays.  N > 1: results stay on the device for the one all-gather, then one D2H.
+        # are numpy arrays.  N > 1: the same chunked call with the results left on the device for the one
+        # all-gather, then one D2H.
         if world == 1:
             res = engine.reduce_batch(A_pin, b_pin, want_A=False, want_b=False)
             return (torch.from_numpy(res.keep), torch.from_numpy(res.flags), torch.from_numpy(res.n_lp),
                     torch.from_numpy(res.lp_iters))
-        res = engine.reduce_batch(A_pin.to('cuda', non_blocking=True), b_pin.to('cuda', non_blocking=True), want_A=False)
+        res = engine.reduce_batch(A_pin, b_pin, want_A=False, want_b=False, results_on_device=True)
         packed = torch.stack([res.keep, res.flags.to(torch.int64), res.n_lp.to(torch.int64),
                               res.lp_iters.to(torch.int64)], 1)
         allp = sharding.allgather_blocks(packed, world * P).cpu()

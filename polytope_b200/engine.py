@@ -198,19 +198,23 @@ class ReduceResult(object):
 
 
 def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True, want_b=True,
-                 non_empty_bounded=True):
+                 non_empty_bounded=True, results_on_device=False):
     """reduce(Polytope(A[p], b[p])) for every p (polytope.py:1053-1163).
 
     normalize=False reproduces reduce(poly) on rows that a constructor already
     normalised (poly.A, poly.b are used as they are).  For host-resident batches
     want_A / want_b = False skip the device-to-host copies of the row data (A; b,
-    r, xc) when only the keep masks, flags and LP counts are wanted.
+    r, xc) when only the keep masks, flags and LP counts are wanted; results_on_device=True
+    leaves the results of a host-resident batch on the GPU (for a collective that follows:
+    the chunked H2D / kernel overlap stays, the D2H is the caller's).
     """
     _require_cuda()
     lib = _capi.lib()
     if _is_host(A) and len(A) >= 2 * PIPELINE_MIN_CHUNK:
-        return _reduce_batch_host_pipelined(A, b, m_rows, abs_tol, normalize, want_A, want_b)
+        return _reduce_batch_host_pipelined(A, b, m_rows, abs_tol, normalize, want_A, want_b, non_empty_bounded,
+                                            results_on_device)
     A, host = _dev(A)
+    host = host and not results_on_device
     b, _ = _dev(b)
     P, m, d = A.shape
     mr, mr_ptr = _opt(m_rows, torch.int32)
@@ -249,6 +253,7 @@ def reduce_batch(A, b, m_rows=None, abs_tol=ABS_TOL, normalize=True, want_A=True
 REDUCE_NO_EARLY_EXIT = 2        # bit 1 of pb200_reduce_batch's `normalize` argument (include/polytope_b200.h)
 PIPELINE_MIN_CHUNK = 1024      # polytopes per chunk below which pipelining does not pay
 PIPELINE_CHUNKS = int(__import__('os').environ.get('PB200_PIPELINE_CHUNKS', '2'))
+PIPELINE_FRACTIONS = None      # e.g. (0.25, 0.75): uneven chunk sizes (overrides PIPELINE_CHUNKS)
 PINNED_CACHE_BYTES = 1 << 30   # cap on cached page-locked staging memory (per process)
 _pinned = {}                   # tag -> flat uint8 pinned buffer (grown geometrically, reused through views)
 _pinned_lock = threading.Lock()
@@ -284,17 +289,19 @@ def _pinned_buffer(tag, shape, dtype):
         return flat[:nbytes].view(dtype).view(shape)
 
 
-def _reduce_batch_host_pipelined(A, b, m_rows, abs_tol, normalize, want_A, want_b, non_empty_bounded=True):
+def _reduce_batch_host_pipelined(A, b, m_rows, abs_tol, normalize, want_A, want_b, non_empty_bounded=True,
+                                 on_device=False):
     """reduce_batch for host-resident batches: the batch is cut into chunks that
     alternate between two CUDA streams, so the H2D copy of chunk k+1 and the D2H
     of chunk k-1 overlap the kernels of chunk k.  Results land in pinned host
     buffers and come back as numpy arrays."""
     with _pipeline_lock:
         return _reduce_batch_host_pipelined_locked(A, b, m_rows, abs_tol, normalize, want_A, want_b,
-                                                   non_empty_bounded)
+                                                   non_empty_bounded, on_device)
 
 
-def _reduce_batch_host_pipelined_locked(A, b, m_rows, abs_tol, normalize, want_A, want_b, non_empty_bounded):
+def _reduce_batch_host_pipelined_locked(A, b, m_rows, abs_tol, normalize, want_A, want_b, non_empty_bounded,
+                                        on_device=False):
     if not _streams:
         _streams.extend([torch.cuda.Stream(), torch.cuda.Stream()])
     At = torch.as_tensor(A)
@@ -306,13 +313,22 @@ def _reduce_batch_host_pipelined_locked(A, b, m_rows, abs_tol, normalize, want_A
     mt = None if m_rows is None else torch.as_tensor(np.ascontiguousarray(m_rows, dtype=np.int32))
     P, m, d = At.shape
     nchunk = max(2, min(PIPELINE_CHUNKS, P // PIPELINE_MIN_CHUNK))
-    bounds = [(P * k // nchunk, P * (k + 1) // nchunk) for k in range(nchunk)]
+    if PIPELINE_FRACTIONS:
+        # uneven chunks: a small first chunk shortens the only copy nothing overlaps
+        cuts = [0] + [int(round(P * f)) for f in np.cumsum(PIPELINE_FRACTIONS)]
+        cuts[-1] = P
+        bounds = [(lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+    else:
+        bounds = [(P * k // nchunk, P * (k + 1) // nchunk) for k in range(nchunk)]
     names = ['keep', 'flags', 'n_lp', 'lp_iters'] + (['r', 'xc', 'b'] if want_b else []) + (['A'] if want_A else [])
     shapes = {'keep': (P,), 'flags': (P,), 'r': (P,), 'xc': (P, d), 'b': (P, m), 'n_lp': (P,), 'lp_iters': (P,),
               'A': (P, m, d)}
     dtypes = {'keep': torch.int64, 'flags': torch.int32, 'r': torch.float64, 'xc': torch.float64, 'b': torch.float64,
               'n_lp': torch.int32, 'lp_iters': torch.int32, 'A': torch.float64}
-    out = {n: _pinned_buffer('reduce_' + n, shapes[n], dtypes[n]) for n in names}
+    if on_device:
+        out = {n: torch.empty(shapes[n], dtype=dtypes[n], device='cuda') for n in names}
+    else:
+        out = {n: _pinned_buffer('reduce_' + n, shapes[n], dtypes[n]) for n in names}
     cur = torch.cuda.current_stream()
     keepalive = []
     for k, (lo, hi) in enumerate(bounds):
@@ -329,8 +345,18 @@ def _reduce_batch_host_pipelined_locked(A, b, m_rows, abs_tol, normalize, want_A
             keepalive.append((Ad, bd, md, res))
     for st in _streams:
         cur.wait_stream(st)
-    cur.synchronize()
     res = ReduceResult()
+    if on_device:
+        # stream-ordered: the caller's stream waits for both pipeline streams, nothing blocks the host; the
+        # chunk buffers are handed to the allocator only after their streams have been joined
+        for Ad, bd, md, _ in keepalive:
+            for t in (Ad, bd, md):
+                if t is not None:
+                    t.record_stream(cur)
+        for n in ReduceResult.__slots__:
+            setattr(res, n, out.get(n))
+        return res
+    cur.synchronize()
     for n in ReduceResult.__slots__:
         setattr(res, n, out[n].numpy().copy() if n in out else None)
     return res

@@ -369,6 +369,11 @@ def test_host_batches_are_pipelined_and_equal_the_device_path():
     # the last bits of an LP's solution depend on which LPs share its warp -- chunking regroups them
     r = dev.r.cpu().numpy()
     np.testing.assert_allclose(np.asarray(host.r), r, rtol=0, atol=1e-12, equal_nan=True)
+    # the same chunked path with the results left on the device (what a sharded caller all-gathers)
+    kept = engine.reduce_batch(A, b, rows, want_A=False, want_b=False, results_on_device=True)
+    assert isinstance(kept.keep, torch.Tensor) and kept.keep.is_cuda and kept.A is None
+    for name in ('keep', 'flags', 'n_lp'):
+        assert torch.equal(getattr(kept, name), getattr(dev, name)), name
     # the Chebyshev centre is not unique (polytope.py:1245-1246): each path's centre must admit the ball
     An, bn = np.asarray(host.A), np.asarray(host.b)
     live = np.arange(m)[None, :] < rows[:, None]
