@@ -13,6 +13,19 @@ Each single-object function has a batched sibling (`*_batch`) that runs the
 whole list in a handful of kernel launches -- that is the form the throughput
 numbers are quoted on.  Operations outside the hot path (projection, esp,
 rotation, plotting) are not provided.
+
+Attribution.  The class shells and the sequential host logic that SURVEY.md 8(f)
+leaves on the host restate code of tulip-control/polytope (polytope/polytope.py,
+Copyright (c) 2011-2014 California Institute of Technology, BSD 3-clause; see
+the reference's LICENSE): `is_convex`, `union`, `is_interior`, `grid_region`,
+`enumerate_integral_points`, the d <= 2 branch of `extreme`
+(`_extreme_low_dim`), the `overlap=False` branch of `is_adjacent`, and the step
+sequence of `reduce` in `_reduce_wide` follow the reference line by line (each
+cites its line range) because the API contract is "the same results for the same
+calls".  Redistribution of this file is under the terms of that licence for
+those parts.  Everything that carries the design -- the `*_batch` functions,
+`region_diff_batch`, `extreme_batch`, `separate`, the device pipelines they
+drive -- is original to this repository.
 """
 import logging
 import math
