@@ -140,6 +140,7 @@ struct RowLanes {
     double abs_tol;
     unsigned long long* keep;   // OR-accumulated
     int32_t* lp_iters;          // nullable: += interior-point iterations
+    static constexpr int kUnroll = 1;      // row loops of the solver not unrolled: instruction-fetch bound (lp_lane.cuh)
     __device__ int n() const { return d; }
     __device__ int count(long long p) const {
         if (!(flags[p] & run_mask)) return 0;
@@ -183,6 +184,7 @@ struct BboxLanes {
     double *val_lo, *val_hi;     // [P][d] each: optimised coordinate of the lower / upper LP
     int8_t* status;              // [P][2d]
     int32_t* lp_iters;           // nullable: += iterations
+    static constexpr int kUnroll = 2;
     __device__ int n() const { return d; }
     __device__ int count(long long p) const {
         if (need_flags && !(need_flags[p] & need_mask)) return 0;
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(32, NS <= 8 ? PB200_LANE_MINB : 2) lane_kernel
         dat.m = my_rows;
         prob.template setup<NS>(dat, my_k);
         lane::Result<NS> res;
-        if constexpr (NS <= 8) lane::lane_solve<NS, LaneData<NS>, lane::WarpLanes>(dat, my_p >= 0, prob.n(), res);
+        if constexpr (NS <= 8) lane::lane_solve<NS, LaneData<NS>, lane::WarpLanes, Prob::kUnroll>(dat, my_p >= 0, prob.n(), res);
         else lane::lane_solve_wide<NS, LaneData<NS>, lane::WarpLanes>(dat, my_p >= 0, prob.n(), res);
         if (my_p >= 0) prob.template store<NS>(my_p, my_k, res);
         __syncwarp();

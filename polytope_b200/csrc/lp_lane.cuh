@@ -172,8 +172,12 @@ PBL_FN double dotn(const double (&a)[NS], const double (&b)[NS]) {
 #define PBL_STR2(x) #x
 #define PBL_STR(x) PBL_STR2(x)
 #define PBL_ROWS _Pragma(PBL_STR(unroll PB200_LANE_UNROLL))
+// inside lane_solve the row loops unroll by its template parameter UR: the row-LP kernel is instruction-fetch
+// sensitive (ncu: no_instruction 0.87 cycles per issue) and runs 8 % faster with UR = 1, the bounding-box kernel
+// (no_instruction 0.06) 9 % slower (r02ab A/B builds, profiles/r02ab_lane_unroll_ab.txt)
+#define PBL_ROWS_UR _Pragma("unroll UR")
 
-template <int NS, class D, class W>
+template <int NS, class D, class W, int UR = PB200_LANE_UNROLL>
 PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
     constexpr int NT = NS * (NS + 1) / 2;
     const int m = has_lp ? dat.rows() : 0;
@@ -219,7 +223,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                 for (int j = 0; j < NS; ++j) { v1[j] = 0.0; v2[j] = 0.0; v3[j] = 0.0; }
                 double sz = 0.0, hz = 0.0, rz2 = 0.0, gxs2 = 0.0, dhh = 0.0, dhq = 0.0;
-                PBL_ROWS
+                PBL_ROWS_UR
                 for (int i = 0; i < m; ++i) {
                     double g[NS];
                     dat.row(i, g);
@@ -363,7 +367,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                     for (int j = 0; j < NS; ++j) xa[j] = fma(dta, X1[j], xa[j]);
                     double ratio = fmax(fmax(-dta * tinv, -dka * kinv), 0.0);
-                    PBL_ROWS
+                    PBL_ROWS_UR
                     for (int i = 0; i < m; ++i) {            // pass B: affine step length
                         double g[NS];
                         dat.row(i, g);
@@ -383,7 +387,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                     double dhqc = 0.0;
 #pragma unroll
                     for (int j = 0; j < NS; ++j) X3[j] = 0.0;
-                    PBL_ROWS
+                    PBL_ROWS_UR
                     for (int i = 0; i < m; ++i) {
                         double g[NS];
                         dat.row(i, g);
@@ -418,7 +422,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                     for (int j = 0; j < NS; ++j) X3[j] = fma(dtau, X1[j], X3[j]);
                     ratio = fmax(fmax(-dtau * tinv, -dkap * kinv), 0.0);
-                    PBL_ROWS
+                    PBL_ROWS_UR
                     for (int i = 0; i < m; ++i) {            // pass D: step length
                         double g[NS];
                         dat.row(i, g);
@@ -439,7 +443,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                     }
                     const double amax = ratio > 0.0 ? rcp(ratio) : 1e30;
                     const double alpha = fmin(1.0, STEP * amax);
-                    PBL_ROWS
+                    PBL_ROWS_UR
                     for (int i = 0; i < m; ++i) {            // pass E: take the step in (s, z)
                         double g[NS];
                         dat.row(i, g);
@@ -522,7 +526,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                     for (int j = 0; j < NS; ++j) { vp[j] = 0.0; vd[j] = 0.0; }
                     double ft = 0.0, fslack = -1e300, fymin = -1e300, fymax = 0.0;
-                    PBL_ROWS
+                    PBL_ROWS_UR
                     for (int i = 0; i < m; ++i) {
                         double g[NS];
                         dat.row(i, g);
