@@ -78,6 +78,7 @@ struct HullWs {
     int32_t* disc;    // [cap] claim of the walk (lowest discovering item), INT_MAX when idle
     int32_t* ppos;    // [cap] per cone facet k: position of the new point in its sorted vertex list
     int32_t* redo;    // [cap] cone facets whose pencil plane failed the check (rebuilt by Gauss-Jordan)
+    unsigned long long* ikey;   // [IKEY_CAP] 64-bit key of the cone ridge (facet k, position i) at k * d + i
     int32_t* vis_list;  // [cap]
     int32_t* hor_list;  // [cap] ridge items f*d+i
     int32_t* new_list;  // [cap] slots of the new facets
@@ -90,7 +91,17 @@ struct HullWs {
     int32_t* cand;    // [Nmax] first new facet (index into new_list) an orphan is outside of
 };
 
+constexpr int IKEY_CAP = 1 << 16;    // cone ridges with precomputed keys; larger cones hash the vertex rows
 __host__ __device__ inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+// 64-bit mix of a vertex id (splitmix64 finaliser).  The key of a ridge is the SUM of the mixes of its vertices: all
+// d - 1 keys of a new facet come from one total by subtraction, and equal vertex sets give equal keys whatever the
+// order.  Two different (d-2)-sets collide with probability ~2^-64 per comparison.
+__device__ __forceinline__ unsigned long long vmix(int v) {
+    unsigned long long x = (unsigned long long)(unsigned)v + 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
 __host__ __device__ inline unsigned table_cap(int cap, int d) {
     unsigned need = 2u * (unsigned)cap * (unsigned)d;
     unsigned t = 1024;
@@ -104,6 +115,7 @@ __host__ __device__ inline size_t hull_ws_bytes(int Nmax, int d, int cap, int x_
     s += 2 * align_up(sizeof(int32_t) * (size_t)d * cap);
     s += 5 * align_up(sizeof(int32_t) * (size_t)cap);
     s += 4 * align_up(sizeof(int32_t) * (size_t)cap);
+    s += align_up(sizeof(unsigned long long) * (size_t)IKEY_CAP);
     s += align_up(sizeof(uint32_t) * (size_t)table_cap(cap, d));
     if (!x_in_smem) s += align_up(sizeof(double) * (size_t)d * Nmax);
     s += 3 * align_up(sizeof(int32_t) * (size_t)Nmax);
@@ -122,6 +134,7 @@ __device__ inline HullWs hull_carve(char* p, int Nmax, int d, int cap, int x_in_
     w.disc = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
     w.ppos = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
     w.redo = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
+    w.ikey = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)IKEY_CAP);
     w.vis_list = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
     w.hor_list = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
     w.new_list = (int32_t*)take(sizeof(int32_t) * (size_t)cap);
@@ -586,6 +599,7 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         // (|n . v - off| <= 1e-13 max(1, |n|.|v|) for all d of them, so no error is inherited from the parent planes); a facet
         // that fails -- nearly coplanar parents -- is rebuilt from its vertices by Gauss-Jordan below.
         int nRedo = 0;
+        const bool keyed = (long long)nH * d <= IKEY_CAP;
         {
             for (int k0 = 0; k0 < nH; k0 += HT) {
                 const int k = k0 + tid;
@@ -597,11 +611,19 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
                     const int g = w.new_list[k];
                     int vv[D];
                     int pos = 0;
+                    unsigned long long ktot = 0;
 #pragma unroll
                     for (int t = 0; t < D - 1; ++t) {
                         const int e = ridge_elem(w.vid, d, f, i, t);
                         pos += e < pstar ? 1 : 0;
                         vv[t] = e;
+                        ktot += vmix(e);
+                    }
+                    if (keyed) {
+                        // key of the cone ridge that omits ridge vertex t (and pstar), stored at the vertex's
+                        // position in the new facet's sorted list
+#pragma unroll
+                        for (int t = 0; t < D - 1; ++t) w.ikey[(size_t)k * d + t + (t >= pos ? 1 : 0)] = ktot - vmix(vv[t]);
                     }
                     const double* nf = w.nrm + (size_t)f * D;
                     const double* ng = w.nrm + (size_t)gout * D;
@@ -672,7 +694,9 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
         }
         // (measured r02t / r02u, 1000 cfg4 duals: one thread per new FACET with the vertex row in registers 75 ms,
         // the ridge table in shared memory 38 ms -- 64 KB per CTA cost more L1 than the faster atomics gained --
-        // against 28 ms for this form: one thread per (facet, ridge), table in global memory)
+        // against 28 ms for one thread per (facet, ridge) with the table in global memory; precomputed 64-bit
+        // ridge keys then shorten every probe from five dependent memory round trips to three: 25 ms, 23.9 ms with
+        // four CTAs per SM; four ridges in flight per thread on top of that changed nothing, r02ag)
         // (e2) neighbour pointers of the cone.  Across the horizon ridge (the one that omits pstar): the
         // facet outside, whose own pointer moves from the visible facet to the new one.  Across the d - 1
         // ridges that contain pstar: another new facet, found by hashing the ridge without pstar -- the first
@@ -681,6 +705,28 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
             const int k = t / d, i = t - k * d;
             const int g = w.new_list[k];
             const int pos = w.ppos[k];
+            if (keyed && i != pos) {
+                // the key of this ridge was left by the thread that built the facet: the probe touches the
+                // table and the other item's key only, no vertex rows
+                const unsigned long long key = w.ikey[t];
+                uint32_t slot = ((uint32_t)(key >> 32) ^ (uint32_t)key) * 0x85ebca6bu;
+                slot = (slot ^ (slot >> 15)) & (tsize - 1);
+                const uint32_t me = (uint32_t)t + 1u;
+                for (unsigned probe = 0; probe < tsize; ++probe) {
+                    const uint32_t cur = atomicCAS(w.table + slot, 0u, me);
+                    if (cur == 0u) break;
+                    const int t2 = (int)(cur - 1u);
+                    if (w.ikey[t2] == key) {
+                        const int k2 = t2 / d;
+                        const int g2 = w.new_list[k2];
+                        w.nbr[(size_t)g * D + i] = g2;
+                        w.nbr[(size_t)g2 * D + (t2 - k2 * d)] = g;
+                        break;
+                    }
+                    slot = (slot + 1) & (tsize - 1);
+                }
+                continue;
+            }
             if (i == pos) {
                 const int item = w.hor_list[k];
                 const int f = item / d;
@@ -788,8 +834,11 @@ __device__ void hull_one(const HullArgs& a, const HullWs& w, int h, BlockScratch
     finish(HS_OK, nF, o, inserted, created);
 }
 
+#ifndef PB200_HULL_MINB
+#define PB200_HULL_MINB 4
+#endif
 template <int D>
-__global__ void __launch_bounds__(HT, 3) hull_kernel(const HullArgs a) {
+__global__ void __launch_bounds__(HT, PB200_HULL_MINB) hull_kernel(const HullArgs a) {
     extern __shared__ __align__(16) double smem_x[];
     __shared__ BlockScratch bs;
     __shared__ double sh_p[HULL_MAX_D], sh_c[HULL_MAX_D], sh_q[HULL_MAX_D * HULL_MAX_D];
@@ -819,7 +868,7 @@ static int launch_hull(const HullArgs& a, int grid, size_t smem, cudaStream_t st
 static int hull_grid(int H) {
     const int sms = sm_count();
     if (!sms) return 0;
-    const int g = 3 * sms;
+    const int g = PB200_HULL_MINB * sms;
     return H < g ? H : g;
 }
 static int hull_x_in_smem(int Nmax, int d) { return (size_t)Nmax * d * sizeof(double) <= 96 * 1024 ? 1 : 0; }
