@@ -381,20 +381,25 @@ def strong_scaling(torch, dist, engine, sharding, rank, world, barrier, reps=5):
     cfg5 (prop2partition adjacency grid, all ordered pairs as MetricPartition.compute_adj walks
     them, prop2partition.py:253-261) and cfg4 (extreme() of 1 000 polytopes d = 12, m = 64).
     Each rank does its contiguous block of pairs / polytopes; one all-gather of the flags, and of
-    the vertex counts + (ragged) vertices.  Device-timed with CUDA events, max over ranks."""
+    the vertex counts + (ragged) vertices.  Device-timed with CUDA events (median of the repetitions), max over ranks."""
     out = {}
 
     def run(fn, reps):
+        # every repetition has its own event pair and the median is reported: these calls are a few milliseconds
+        # long, and one host-side hiccup (allocator growth, garbage collection) inside a single bracket around all
+        # repetitions moved the figure by an order of magnitude between runs
         fn()
         fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        times = []
         for _ in range(reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             res = fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device='cuda')
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = torch.tensor([sorted(times)[len(times) // 2]], dtype=torch.float64, device='cuda')
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), res
