@@ -140,7 +140,10 @@ struct RowLanes {
     double abs_tol;
     unsigned long long* keep;   // OR-accumulated
     int32_t* lp_iters;          // nullable: += interior-point iterations
-    static constexpr int kUnroll = 1;      // row loops of the solver not unrolled: instruction-fetch bound (lp_lane.cuh)
+    struct Tune {                          // lp_lane.cuh: the row-LP kernel is instruction-fetch bound
+        static constexpr int kUnroll = 1;
+        static constexpr double kEarly = 1e-1, kNext = 1e-1;
+    };
     __device__ int n() const { return d; }
     __device__ int count(long long p) const {
         if (!(flags[p] & run_mask)) return 0;
@@ -184,7 +187,10 @@ struct BboxLanes {
     double *val_lo, *val_hi;     // [P][d] each: optimised coordinate of the lower / upper LP
     int8_t* status;              // [P][2d]
     int32_t* lp_iters;           // nullable: += iterations
-    static constexpr int kUnroll = 2;
+    struct Tune {                          // unit objectives: the active set shows after the first iteration
+        static constexpr int kUnroll = 2;
+        static constexpr double kEarly = 1.0, kNext = 1e-1;
+    };
     __device__ int n() const { return d; }
     __device__ int count(long long p) const {
         if (need_flags && !(need_flags[p] & need_mask)) return 0;
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(32, NS <= 8 ? PB200_LANE_MINB : 2) lane_kernel
         dat.m = my_rows;
         prob.template setup<NS>(dat, my_k);
         lane::Result<NS> res;
-        if constexpr (NS <= 8) lane::lane_solve<NS, LaneData<NS>, lane::WarpLanes, Prob::kUnroll>(dat, my_p >= 0, prob.n(), res);
+        if constexpr (NS <= 8) lane::lane_solve<NS, LaneData<NS>, lane::WarpLanes, typename Prob::Tune>(dat, my_p >= 0, prob.n(), res);
         else lane::lane_solve_wide<NS, LaneData<NS>, lane::WarpLanes>(dat, my_p >= 0, prob.n(), res);
         if (my_p >= 0) prob.template store<NS>(my_p, my_k, res);
         __syncwarp();

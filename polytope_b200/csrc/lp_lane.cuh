@@ -34,10 +34,13 @@ constexpr double STEP = 0.99;
 constexpr double STALL_DRES = 1e-6;   // see the termination test
 constexpr double STALL_GAP = 1e-13;
 #ifndef PB200_LANE_EARLY_TOL
-#define PB200_LANE_EARLY_TOL 1e-2
+#define PB200_LANE_EARLY_TOL 1e-1
 #endif
 constexpr double EARLY_TOL = PB200_LANE_EARLY_TOL;   // residual level of the first certified-polish attempt
-constexpr double EARLY_NEXT = 1e-2;                   // a failed attempt is repeated after this much progress
+#ifndef PB200_LANE_EARLY_NEXT
+#define PB200_LANE_EARLY_NEXT 1e-1
+#endif
+constexpr double EARLY_NEXT = PB200_LANE_EARLY_NEXT;  // a failed attempt is repeated after this much progress
 #ifndef PB200_LANE_MAX_WAIT
 #define PB200_LANE_MAX_WAIT 2
 #endif
@@ -89,6 +92,21 @@ struct WarpLanes {
     static __device__ __forceinline__ bool any_busy(bool p) { return __any_sync(0xffffffffu, p); }
 };
 #endif
+
+#ifndef PB200_LANE_UNROLL
+#define PB200_LANE_UNROLL 2
+#endif
+// Per-family tuning of lane_solve (r02ab / r02ak A/B builds on cfg2, profiles/r02ak_lane_early_polish_ab.txt).
+//   kUnroll  unroll factor of the row loops (the row-LP kernel is instruction-fetch bound: 1)
+//   kEarly   residual level at which the certified polish is first tried.  The certificate makes any
+//            attempt safe (a point is only accepted as a complementary primal-dual optimal pair), so this
+//            is purely a speed knob: 1e-2 -> 1e-1 cut the mean iterations per LP from 4.4 to 3.5
+//   kNext    a failed attempt is repeated after this much further progress
+struct DefaultTune {
+    static constexpr int kUnroll = PB200_LANE_UNROLL;
+    static constexpr double kEarly = EARLY_TOL;
+    static constexpr double kNext = EARLY_NEXT;
+};
 
 template <int NS>
 struct Result {
@@ -177,8 +195,9 @@ PBL_FN double dotn(const double (&a)[NS], const double (&b)[NS]) {
 // (no_instruction 0.06) 9 % slower (r02ab A/B builds, profiles/r02ab_lane_unroll_ab.txt)
 #define PBL_ROWS_UR _Pragma("unroll UR")
 
-template <int NS, class D, class W, int UR = PB200_LANE_UNROLL>
+template <int NS, class D, class W, class Tune = DefaultTune>
 PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
+    constexpr int UR = Tune::kUnroll;
     constexpr int NT = NS * (NS + 1) / 2;
     const int m = has_lp ? dat.rows() : 0;
     res.status = ITER_LIMIT; res.iters = 0; res.polishes = 0; res.fun = 0.0;
@@ -207,7 +226,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
     const double rmu = 1.0 / (double)(m + 1);
     double tau = 1.0, kap = 1.0;
     bool lineal = false, ready = false;     // lineal: the objective has been dropped (feasibility problem, c = 0)
-    double etol = EARLY_TOL;
+    double etol = Tune::kEarly;
     int phase = has_lp ? PH_IPM : PH_DONE, it = 0, waited = 0;
 
     for (;;) {
@@ -481,7 +500,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
             ++res.polishes;
             waited = 0;
             ready = false;
-            if (early) etol *= EARLY_NEXT;
+            if (early) etol *= Tune::kNext;
             const double te = 1.0 / tau;
             double xp[NS];
 #pragma unroll

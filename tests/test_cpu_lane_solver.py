@@ -67,7 +67,7 @@ def test_lps_of_reduce(cfg, m, d, ss, npoly):
     st = np.array([r[3] for r in rec], dtype=np.int32)
     fun = np.array([np.nan if r[4] is None else r[4] for r in rec])
     it, pol = _check(lps, st, fun, tol=1e-9)
-    assert it.mean() < 6 and pol.max() <= 3
+    assert it.mean() < 6 and pol.max() <= 5      # certified-polish attempts start at a residual level of 0.1 and repeat every 10x
 
 
 def test_random_lps_every_status_against_highs():
