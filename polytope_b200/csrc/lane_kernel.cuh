@@ -142,7 +142,13 @@ struct RowLanes {
     int32_t* lp_iters;          // nullable: += interior-point iterations
     struct Tune {                          // lp_lane.cuh: the row-LP kernel is instruction-fetch bound
         static constexpr int kUnroll = 1;
-        static constexpr double kEarly = 1e-1, kNext = 1e-1;
+#ifndef PB200_ROW_EARLY
+#define PB200_ROW_EARLY 1e-1
+#endif
+#ifndef PB200_ROW_NEXT
+#define PB200_ROW_NEXT 1e-1
+#endif
+        static constexpr double kEarly = PB200_ROW_EARLY, kNext = PB200_ROW_NEXT;
     };
     __device__ int n() const { return d; }
     __device__ int count(long long p) const {

@@ -30,7 +30,10 @@ namespace lane {
 constexpr int MAX_ITER = 60;
 constexpr double FEAS_TOL = 1e-9;
 constexpr double GAP_TOL = 1e-9;
-constexpr double STEP = 0.99;
+#ifndef PB200_LANE_STEP
+#define PB200_LANE_STEP 0.999      // fraction of the step to the boundary (r02ap: 0.99 -> 0.999 is 4 % on cfg2; the certified exit tolerates it)
+#endif
+constexpr double STEP = PB200_LANE_STEP;
 constexpr double STALL_DRES = 1e-6;   // see the termination test
 constexpr double STALL_GAP = 1e-13;
 #ifndef PB200_LANE_EARLY_TOL
@@ -42,7 +45,7 @@ constexpr double EARLY_TOL = PB200_LANE_EARLY_TOL;   // residual level of the fi
 #endif
 constexpr double EARLY_NEXT = PB200_LANE_EARLY_NEXT;  // a failed attempt is repeated after this much progress
 #ifndef PB200_LANE_MAX_WAIT
-#define PB200_LANE_MAX_WAIT 2
+#define PB200_LANE_MAX_WAIT 3
 #endif
 constexpr int MAX_WAIT = PB200_LANE_MAX_WAIT;         // iterations a polish-ready lane waits for the others
 enum : int { OPTIMAL = 0, ITER_LIMIT = 1, INFEASIBLE = 2, UNBOUNDED = 3, NUMERICAL = 4 };   // scipy codes
@@ -538,7 +541,10 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                 for (int j = 0; j < NS; ++j) U[j] = 0.0;
                 const double scale = fmax(1.0, hmax);
-                for (int round = 0; round < 4; ++round) {
+#ifndef PB200_LANE_ROUNDS
+#define PB200_LANE_ROUNDS 3        // projection / refinement rounds of one polish attempt
+#endif
+                for (int round = 0; round < PB200_LANE_ROUNDS; ++round) {
                     // one projection round of the primal point onto the active face and one
                     // least-squares refinement of the multipliers y = z/tau - G_B U share the pass
                     double vp[NS], vd[NS];
@@ -565,7 +571,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                     for (int j = 0; j < NS; ++j) { vd[j] += c0[j]; frd = fmax(frd, fabs(vd[j])); }      // |G_B'y + c|
                     const bool feasible = fslack <= 1e-9 * scale;
-                    const bool settled = ft <= 1e-13 * scale || round == 3;
+                    const bool settled = ft <= 1e-13 * scale || round == PB200_LANE_ROUNDS - 1;
                     if (!early) {
                         if (settled) {
                             const double f1 = dotn<NS>(c0, xp);
@@ -587,7 +593,7 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
                             phase = PH_DONE;
                             break;
                         }
-                        if (round == 3) break;       // not certified: the interior-point iterations resume
+                        if (round == PB200_LANE_ROUNDS - 1) break;       // not certified: the interior-point iterations resume
                     }
                     chol_solve<NS>(M, vp);
                     chol_solve<NS>(M, vd);
