@@ -136,6 +136,7 @@ struct RowLanes {
     uint32_t run_mask;          // run only when (flags & run_mask)
     uint32_t retry_bit;         // set on flags[p] when an LP ends without a verdict (status 1 / 4): the
                                 // polytope's row LPs are then repeated on the warp-per-LP kernel
+    uint32_t* retry_any;        // nullable: set to 1 with it (the retry launch returns at once while it is 0)
     int m, d;
     double abs_tol;
     unsigned long long* keep;   // OR-accumulated
@@ -176,6 +177,7 @@ struct RowLanes {
             kept = true;
         } else if (res.status != lane::INFEASIBLE) {
             atomicOr(flags + p, retry_bit);
+            if (retry_any) *retry_any = 1u;
         }
         if (kept) atomicOr(keep + p, 1ull << orig);
         if (lp_iters) atomicAdd(lp_iters + p, res.iters);
@@ -189,6 +191,7 @@ struct BboxLanes {
     uint32_t* need_flags;        // nullable: run only when (flags & need_mask)
     uint32_t need_mask;
     uint32_t retry_bit;          // with need_flags: set when an LP ends with status 1 / 4 (see RowLanes)
+    uint32_t* retry_any;         // nullable, as RowLanes
     int m, d, renorm;
     double *val_lo, *val_hi;     // [P][d] each: optimised coordinate of the lower / upper LP
     int8_t* status;              // [P][2d]
@@ -226,7 +229,10 @@ struct BboxLanes {
             if (j == i) xi = res.x[j];
         (q < d ? val_lo : val_hi)[p * d + i] = res.status == lane::OPTIMAL ? xi : 0.0;
         status[p * 2 * d + q] = (int8_t)res.status;
-        if (need_flags && (res.status == lane::ITER_LIMIT || res.status == lane::NUMERICAL)) atomicOr(need_flags + p, retry_bit);
+        if (need_flags && (res.status == lane::ITER_LIMIT || res.status == lane::NUMERICAL)) {
+            atomicOr(need_flags + p, retry_bit);
+            if (retry_any) *retry_any = 1u;
+        }
         if (lp_iters) atomicAdd(lp_iters + p, res.iters);
     }
 };

@@ -301,7 +301,8 @@ struct AdjacentLP {
 // the one LP kernel
 // ------------------------------------------------------------------------
 template <int RPL, class Prob>
-__global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long n_items) {
+__global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long n_items, const uint32_t* gate) {
+    if (gate != nullptr && *gate == 0u) return;     // retry launch with nothing to retry (see launch_persistent)
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wib = __reduce_max_sync(FULL_MASK, threadIdx.x >> 5);   // provably uniform
     const int n = prob.n();
@@ -335,7 +336,8 @@ __global__ void __launch_bounds__(WPC * 32) lp_kernel(const Prob prob, long long
 #define PB200_SMALL_MINB 4
 #endif
 template <int RPL, class Prob>
-__global__ void __launch_bounds__(WPC * 32, PB200_SMALL_MINB) lp_kernel_small(const Prob prob, long long n_items) {
+__global__ void __launch_bounds__(WPC * 32, PB200_SMALL_MINB) lp_kernel_small(const Prob prob, long long n_items, const uint32_t* gate) {
+    if (gate != nullptr && *gate == 0u) return;
     extern __shared__ __align__(16) double smem[];
     // warp index through a warp reduction: the result is provably warp-uniform, so the
     // item loop below (and everything it controls) is uniform control flow for ptxas
@@ -383,7 +385,10 @@ static inline void stage_mark(int i, cudaStream_t st) {
 }
 
 template <class Kern, class Prob>
-static int launch_persistent(Kern kern, size_t smem, const Prob& prob, long long n_items, cudaStream_t st) {
+// `gate` (nullable, device): the kernel returns at once when *gate == 0.  The retry launches of the reduce pipeline
+// pass the word the lane kernels set when an LP ended without a verdict: an ungated empty retry launch still walks
+// every item's flag (17 + 31 us per cfg2 step, ncu r02ar).
+static int launch_persistent(Kern kern, size_t smem, const Prob& prob, long long n_items, cudaStream_t st, const uint32_t* gate = nullptr) {
     if (smem > 227 * 1024) return fail(PB200_EUNSUPPORTED, "LP too large for shared memory");
     PB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!sm_count()) return PB200_ECUDA;
@@ -394,29 +399,29 @@ static int launch_persistent(Kern kern, size_t smem, const Prob& prob, long long
     long long grid = (long long)g_sm_count * per_sm;
     const long long need = (n_items + WPC - 1) / WPC;
     if (need < grid) grid = need;
-    kern<<<(unsigned)grid, WPC * 32, smem, st>>>(prob, n_items);
+    kern<<<(unsigned)grid, WPC * 32, smem, st>>>(prob, n_items, gate);
     ++g_launches;
     PB_CHECK_CUDA(cudaGetLastError());
     return PB200_OK;
 }
 
 template <int RPL, class Prob>
-static int launch_lp_rpl(const Prob& prob, long long n_items, int n, cudaStream_t st) {
+static int launch_lp_rpl(const Prob& prob, long long n_items, int n, cudaStream_t st, const uint32_t* gate = nullptr) {
     if (n_items <= 0) return PB200_OK;
     if (n <= NS && RPL <= 2)
         return launch_persistent(lp_kernel_small<(RPL <= 2 ? RPL : 1), Prob>,
-                                 (size_t)WPC * lps_scratch_doubles(RPL) * sizeof(double), prob, n_items, st);
+                                 (size_t)WPC * lps_scratch_doubles(RPL) * sizeof(double), prob, n_items, st, gate);
     return launch_persistent(lp_kernel<RPL, Prob>, (size_t)WPC * lp_scratch_doubles(RPL, n) * sizeof(double), prob,
-                             n_items, st);
+                             n_items, st, gate);
 }
 
 template <class Prob>
-static int launch_lp(const Prob& prob, long long n_items, int m, int n, cudaStream_t st) {
+static int launch_lp(const Prob& prob, long long n_items, int m, int n, cudaStream_t st, const uint32_t* gate = nullptr) {
     if (n < 1 || n > LP_MAX_N) return fail(PB200_EUNSUPPORTED, "number of LP columns must be in 1..32");
     if (m < 1 || m > 128) return fail(PB200_EUNSUPPORTED, "number of LP rows must be in 1..128");
-    if (m <= 32) return launch_lp_rpl<1>(prob, n_items, n, st);
-    if (m <= 64) return launch_lp_rpl<2>(prob, n_items, n, st);
-    return launch_lp_rpl<4>(prob, n_items, n, st);
+    if (m <= 32) return launch_lp_rpl<1>(prob, n_items, n, st, gate);
+    if (m <= 64) return launch_lp_rpl<2>(prob, n_items, n, st, gate);
+    return launch_lp_rpl<4>(prob, n_items, n, st, gate);
 }
 
 // ------------------------------------------------------------------------
@@ -770,6 +775,7 @@ struct ReduceWorkspace {
     uint64_t *valid, *rows1, *rows2;
     unsigned long long* keep_lp;
     int8_t *cheb_status, *bbstatus;
+    uint32_t* retry_any;     // [2]: a bounding-box / row LP of the lane kernels ended without a verdict
     size_t bytes;
 };
 static ReduceWorkspace carve_reduce(void* base, int P, int m, int d) {
@@ -786,6 +792,7 @@ static ReduceWorkspace carve_reduce(void* base, int P, int m, int d) {
     w.keep_lp = (unsigned long long*)take(sizeof(uint64_t) * P);
     w.cheb_status = (int8_t*)take(P);
     w.bbstatus = (int8_t*)take((size_t)P * 2 * d);
+    w.retry_any = (uint32_t*)take(2 * sizeof(uint32_t));
     w.bytes = (size_t)(p - (char*)base);
     return w;
 }
@@ -844,7 +851,7 @@ int pb200_bbox_batch(const double* A, const double* b, const int32_t* m_rows, in
     // resolve kernel then applies the reference's status conventions in place
     int rc;
     if (lane_applies(m, d, P)) {
-        BboxLanes prob{A, b, m_rows, nullptr, nullptr, 0, 0, m, d, 0, lo, hi, status, nullptr};
+        BboxLanes prob{A, b, m_rows, nullptr, nullptr, 0, 0, nullptr, m, d, 0, lo, hi, status, nullptr};
         rc = launch_lanes(prob, P, m, (cudaStream_t)stream);
     } else {
         BboxLP prob{A, b, m_rows, nullptr, nullptr, 0, m, d, 0, lo, hi, status, nullptr};
@@ -879,6 +886,7 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     normalize &= PB200_REDUCE_NORMALIZE;
     int rc;
     if (lp_iters) PB_CHECK_CUDA(cudaMemsetAsync(lp_iters, 0, sizeof(int32_t) * P, st));
+    PB_CHECK_CUDA(cudaMemsetAsync(ws.retry_any, 0, 2 * sizeof(uint32_t), st));
     stage_mark(0, st);
     // 1. constructor normalisation
     rc = launch_normalize(A, b, m_rows, P, m, d, normalize ? 1 : 0, An, ws.bn, ws.valid, st);
@@ -910,12 +918,12 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     stage_mark(3, st);
     // 4. bounding box of Polytope(A_arr, b_arr) where neq > 3 nx
     if (lane_applies(m, d, P)) {
-        BboxLanes bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, CTL_RETRY_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
+        BboxLanes bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, CTL_RETRY_BBOX, ws.retry_any, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
         if ((rc = launch_lanes(bb, P, m, st))) return rc;
         // safety net: polytopes with an LP the lane solver could not finish (none on the BASELINE
         // workloads) go through the warp-per-LP kernel, whose arithmetic differs
         BboxLP again{An, ws.bn, nullptr, ws.rows1, flags, CTL_RETRY_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
-        if ((rc = launch_lp(again, (long long)P * 2 * d, m, d, st))) return rc;
+        if ((rc = launch_lp(again, (long long)P * 2 * d, m, d, st, ws.retry_any))) return rc;
     } else {
         BboxLP bb{An, ws.bn, nullptr, ws.rows1, flags, CTL_NEED_BBOX, m, d, 1, ws.bblo, ws.bbhi, ws.bbstatus, lp_iters};
         if ((rc = launch_lp(bb, (long long)P * 2 * d, m, d, st))) return rc;
@@ -930,10 +938,10 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     // 6. one LP per surviving row
     PB_CHECK_CUDA(cudaMemsetAsync(ws.keep_lp, 0, sizeof(uint64_t) * P, st));
     if (lane_applies(m, d, P)) {
-        RowLanes row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, CTL_RETRY_ROWS, m, d, abs_tol, ws.keep_lp, lp_iters};
+        RowLanes row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, CTL_RETRY_ROWS, ws.retry_any + 1, m, d, abs_tol, ws.keep_lp, lp_iters};
         if ((rc = launch_lanes(row, P, m, st))) return rc;
         RowLP again{An, ws.bn, ws.rows2, flags, CTL_RETRY_ROWS, m, d, abs_tol, ws.keep_lp, lp_iters};
-        if ((rc = launch_lp(again, (long long)P * m, m, d, st))) return rc;
+        if ((rc = launch_lp(again, (long long)P * m, m, d, st, ws.retry_any + 1))) return rc;
     } else {
         RowLP row{An, ws.bn, ws.rows2, flags, CTL_ROW_LOOP, m, d, abs_tol, ws.keep_lp, lp_iters};
         if ((rc = launch_lp(row, (long long)P * m, m, d, st))) return rc;

@@ -31,7 +31,7 @@ def test_library_is_sm100a_with_fp64_mma():
     from polytope_b200 import _capi
     out = subprocess.run(['cuobjdump', '-lelf', _capi.LIB_PATH], capture_output=True, text=True).stdout
     assert 'sm_100a' in out, out
-    sass = subprocess.run(['cuobjdump', '-sass', '-fun', '_ZN5pb2009lp_kernelILi1ENS_5RowLPEEEvT0_x',
+    sass = subprocess.run(['cuobjdump', '-sass', '-fun', '_ZN5pb2009lp_kernelILi1ENS_5RowLPEEEvT0_xPKj',
                            _capi.LIB_PATH], capture_output=True, text=True).stdout
     assert 'DMMA' in sass
 
