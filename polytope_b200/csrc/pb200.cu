@@ -585,8 +585,11 @@ __global__ void prefilter_kernel(const double* __restrict__ An, const double* __
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
     if (p >= P) return;
-    double* an = sh + (size_t)wib * (m * d + 2 * m);   // a_normed [m][d]
-    double* bs = an + m * d;                           // b * a_norm
+    // a_normed [m][ld], ld odd: lane j reads row j in the pair loop, and an even stride of d doubles put the 32 rows
+    // on two banks (16-way conflict: this kernel took 64 us on cfg2 with d = 8)
+    const int ld = d | 1;
+    double* an = sh + (size_t)wib * (m * ld + 2 * m);
+    double* bs = an + m * ld;                          // b * a_norm
     const double* Ap = An + (size_t)p * m * d;
     const double* bp = bn + (size_t)p * m;
     // ABS_TOL of is_fulldim's default argument, polytope.py:962 (not reduce's abs_tol)
@@ -604,7 +607,7 @@ __global__ void prefilter_kernel(const double* __restrict__ An, const double* __
             fin = bi != __longlong_as_double(0x7ff0000000000000ll);
             const double* row = Ap + (size_t)i * d;
             const double an_i = __ddiv_rn(1.0, sqrt(np_sum_squares([&](int j) { return row[j]; }, d)));
-            for (int j = 0; j < d; ++j) an[i * d + j] = __dmul_rn(row[j], an_i);
+            for (int j = 0; j < d; ++j) an[i * ld + j] = __dmul_rn(row[j], an_i);
             bs[i] = __dmul_rn(bi, an_i);
         }
         const unsigned bal = __ballot_sync(FULL_MASK, fin);
@@ -618,7 +621,7 @@ __global__ void prefilter_kernel(const double* __restrict__ An, const double* __
         for (int j = i + 1 + lane; j < m; j += 32) {
             if (!((alive >> j) & 1ull)) continue;
             double dot = 0.0;
-            for (int q = 0; q < d; ++q) dot = fma(an[i * d + q], an[j * d + q], dot);
+            for (int q = 0; q < d; ++q) dot = fma(an[i * ld + q], an[j * ld + q], dot);
             if (dot > 1.0 - abs_tol) {
                 const int rm = bs[i] < bs[j] ? j : i;
                 if (rm < 32) rem_lo |= 1u << rm; else rem_hi |= 1u << (rm - 32);
@@ -904,7 +907,7 @@ int pb200_reduce_batch(const double* A, const double* b, const int32_t* m_rows, 
     // 3. b == inf drop + duplicate-direction filter, then plan
     {
         const int wpb = 4;
-        const size_t sh = (size_t)wpb * (m * d + 2 * m) * sizeof(double);
+        const size_t sh = (size_t)wpb * (m * (d | 1) + 2 * m) * sizeof(double);
         if (sh > 48 * 1024)
             PB_CHECK_CUDA(cudaFuncSetAttribute(prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
         prefilter_kernel<<<blocks_for(P, wpb), wpb * 32, sh, st>>>(An, ws.bn, ws.valid, r, ws.cheb_status, P, m, d,
