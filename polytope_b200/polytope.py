@@ -455,47 +455,48 @@ def _reduce_wide(poly, nonEmptyBounded, abs_tol):
     one rounding away from b (:1147-1149); the right-hand sides below carry exactly that."""
     if not is_fulldim(poly):
         return Polytope()
-    keep_row = np.nonzero(poly.b != np.inf)
-    A_arr, b_arr = poly.A[keep_row], poly.b[keep_row]
-    neq = A_arr.shape[0]
-    a_norm = 1 / np.sqrt(np.sum(A_arr.T**2, 0))
-    a_normed = np.dot(A_arr.T, np.diag(a_norm)).T
-    # candidate pairs from one matrix product, each confirmed by the reference's own 1-D np.dot (:1102)
-    close = np.triu(a_normed.dot(a_normed.T) > 1 - abs_tol - 1e-9, 1)
-    remove_row = []
-    for i, j in zip(*np.nonzero(close)):
-        if np.dot(a_normed[i].T, a_normed[j]) > 1 - abs_tol:
-            remove_row.append(j if b_arr[i] * a_norm[i] < b_arr[j] * a_norm[j] else i)
-    keep_row = np.setdiff1d(range(neq), remove_row).tolist()
-    A_arr, b_arr = A_arr[keep_row], b_arr[keep_row]
-    neq, nx = A_arr.shape
-    if nonEmptyBounded and neq <= nx + 1:
-        return Polytope(A_arr, b_arr)
-    if neq > 3 * nx:
-        lb, ub = Polytope(A_arr, b_arr).bounding_box
-        cand = ~ (np.dot((A_arr > 0) * A_arr, ub - lb) - (np.array([b_arr]).T - np.dot(A_arr, lb)) < -1e-4)
-        A_arr, b_arr = A_arr[cand.squeeze()], b_arr[cand.squeeze()]
-    neq, nx = A_arr.shape
-    if nonEmptyBounded and neq <= nx + 1:
-        return Polytope(A_arr, b_arr)
-    A_arr = np.ascontiguousarray(A_arr)
-    drift = (b_arr + 0.1) - 0.1
-    keep_row = []
-    chunk = max(1, (64 << 20) // (8 * neq))           # right-hand sides of one call: <= 64 MB
-    for k0 in range(0, neq, chunk):
-        ks = np.arange(k0, min(neq, k0 + chunk))
-        H = np.where(np.arange(neq)[None, :] < ks[:, None], drift[None, :], b_arr[None, :])
-        H[np.arange(len(ks)), ks] = b_arr[ks] + 0.1
-        status, _, fun, _ = engine.lp_batch(-A_arr[ks], A_arr, H)
+    finite = poly.b != np.inf                                   # :1087-1089
+    R, rhs = poly.A[finite], poly.b[finite]
+    # duplicate directions (:1094-1109).  The reference scans all pairs with a 1-D np.dot; here one matrix
+    # product proposes the pairs and the reference's own dot confirms each, so the removed set is identical.
+    scale = 1 / np.sqrt(np.sum(R.T**2, 0))
+    unit = np.dot(R.T, np.diag(scale)).T
+    proposed = np.triu(unit.dot(unit.T) > 1 - abs_tol - 1e-9, 1)
+    drop = set()
+    for i, j in zip(*np.nonzero(proposed)):
+        if np.dot(unit[i].T, unit[j]) > 1 - abs_tol:
+            drop.add(j if rhs[i] * scale[i] < rhs[j] * scale[j] else i)
+    left = [k for k in range(len(rhs)) if k not in drop]
+    R, rhs = R[left], rhs[left]
+    nrow, nx = R.shape
+    small = lambda count: bool(nonEmptyBounded) and count <= nx + 1      # noqa: E731  (:1113-1116, :1135-1138)
+    if small(nrow):
+        return Polytope(R, rhs)
+    if nrow > 3 * nx:                                            # rows that cannot touch the bounding box (:1118-1134)
+        lo, hi = Polytope(R, rhs).bounding_box
+        reach = np.dot((R > 0) * R, hi - lo) - (np.array([rhs]).T - np.dot(R, lo))
+        inside = ~(reach < -1e-4)
+        R, rhs = R[inside.squeeze()], rhs[inside.squeeze()]
+        nrow = R.shape[0]
+    if small(nrow):
+        return Polytope(R, rhs)
+    # one LP per remaining row, all in calls that share G (:1142-1160): objective -R[k], row k relaxed by 0.1;
+    # rows before k already carry the (b + 0.1) - 0.1 rounding of the reference's in-place update
+    R = np.ascontiguousarray(R)
+    settled = (rhs + 0.1) - 0.1
+    kept = []
+    per_call = max(1, (64 << 20) // (8 * nrow))                 # right-hand sides of one call: <= 64 MB
+    for first in range(0, nrow, per_call):
+        ks = np.arange(first, min(nrow, first + per_call))
+        H = np.where(np.arange(nrow)[None, :] < ks[:, None], settled[None, :], rhs[None, :])
+        H[np.arange(len(ks)), ks] = rhs[ks] + 0.1
+        status, _, fun, _ = engine.lp_batch(-R[ks], R, H)
         for t, k in enumerate(ks):
-            if status[t] == 0:
-                if -fun[t] - drift[k] > abs_tol:
-                    keep_row.append(int(k))
-            elif status[t] == 3:
-                keep_row.append(int(k))
-    polyOut = Polytope(A_arr[keep_row], drift[keep_row])
-    polyOut.minrep = True
-    return polyOut
+            if status[t] == 3 or (status[t] == 0 and -fun[t] - settled[k] > abs_tol):
+                kept.append(int(k))
+    out = Polytope(R[kept], settled[kept])
+    out.minrep = True
+    return out
 
 
 def reduce_batch(polys, abs_tol=ABS_TOL, nonEmptyBounded=1):
