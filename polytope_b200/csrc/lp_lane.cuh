@@ -34,6 +34,9 @@ constexpr double GAP_TOL = 1e-9;
 #define PB200_LANE_STEP 0.999      // fraction of the step to the boundary (r02ap: 0.99 -> 0.999 is 4 % on cfg2; the certified exit tolerates it)
 #endif
 constexpr double STEP = PB200_LANE_STEP;
+#ifndef PB200_LANE_ROUNDS
+#define PB200_LANE_ROUNDS 3        // projection / refinement rounds of one polish attempt
+#endif
 constexpr double STALL_DRES = 1e-6;   // see the termination test
 constexpr double STALL_GAP = 1e-13;
 #ifndef PB200_LANE_EARLY_TOL
@@ -541,9 +544,6 @@ PBL_FN void lane_solve(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                 for (int j = 0; j < NS; ++j) U[j] = 0.0;
                 const double scale = fmax(1.0, hmax);
-#ifndef PB200_LANE_ROUNDS
-#define PB200_LANE_ROUNDS 3        // projection / refinement rounds of one polish attempt
-#endif
                 for (int round = 0; round < PB200_LANE_ROUNDS; ++round) {
                     // one projection round of the primal point onto the active face and one
                     // least-squares refinement of the multipliers y = z/tau - G_B U share the pass

@@ -465,7 +465,7 @@ PBL_FN void lane_solve_wide(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                 for (int j = 0; j < NS; ++j) U[j] = 0.0;
                 const double scale = fmax(1.0, hmax);
-                for (int round = 0; round < 4; ++round) {
+                for (int round = 0; round < PB200_LANE_ROUNDS; ++round) {
                     double vv[2][NS];
                     double (&vp)[NS] = vv[0];
                     double (&vd)[NS] = vv[1];
@@ -492,7 +492,7 @@ PBL_FN void lane_solve_wide(D& dat, bool has_lp, int n, Result<NS>& res) {
 #pragma unroll
                     for (int j = 0; j < NS; ++j) { vd[j] += c0[j]; frd = fmax(frd, fabs(vd[j])); }
                     const bool feasible = fslack <= 1e-9 * scale;
-                    const bool settled = ft <= 1e-13 * scale || round == 3;
+                    const bool settled = ft <= 1e-13 * scale || round == PB200_LANE_ROUNDS - 1;
                     if (!early) {
                         if (settled) {
                             const double f1 = dotw<NS>(c0, xp);
@@ -513,7 +513,7 @@ PBL_FN void lane_solve_wide(D& dat, bool has_lp, int n, Result<NS>& res) {
                             phase = PH_DONE;
                             break;
                         }
-                        if (round == 3) break;
+                        if (round == PB200_LANE_ROUNDS - 1) break;
                     }
                     chol_solve_mem<NS, 2>(dat, vv);
 #pragma unroll
