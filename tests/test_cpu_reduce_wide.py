@@ -89,3 +89,23 @@ def test_reduce_wide_duplicates_and_early_exit(oracle_lp_batches):
     Ak, bk, _ = orc.normalize_rows(An[o['keep']], o['b'])
     assert np.array_equal(red.A, Ak) and np.array_equal(red.b, bk)
     assert len(red.b) == 4
+
+
+def test_adjacency_of_wide_cells_stacks_the_pairs_on_the_host(oracle_lp_batches):
+    """Cells with more than 32 rows: `adjacency_matrix` builds the stacked, inflated polytope of is_adjacent
+    (polytope.py:1856-1866) per pair and asks for one batch of Chebyshev LPs; flags equal the oracle's."""
+    import polytope_b200 as pc
+    from oracle import polytope_oracle as orc
+    rng = np.random.default_rng(7)
+    cells = []
+    for k in range(4):
+        lo = np.array([float(k if k < 3 else 6), 0.0, 0.0])
+        C = rng.standard_normal((34, 3))
+        C /= np.linalg.norm(C, axis=1)[:, None]
+        A = np.vstack([np.eye(3), -np.eye(3), C])
+        b = np.hstack([lo + 1.0, -lo, C @ (lo + 0.5) + 3.0])
+        cells.append(pc.Polytope(A, b))
+    assert all(c.A.shape[0] == 40 for c in cells)
+    adj = pc.adjacency_matrix(cells)
+    assert np.array_equal(adj, orc.adjacency_matrix([(c.A, c.b) for c in cells]))
+    assert adj[0, 1] == 1 and adj[1, 2] == 1 and adj[0, 2] == 0 and adj[2, 3] == 0
